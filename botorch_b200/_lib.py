@@ -1,0 +1,129 @@
+"""ctypes binding of the C-ABI library `csrc/libmcacq_b200.so` (see include/mcacq_b200.h).
+
+The library is plain C ABI (device pointers + sizes + stream); torch is only used here for device
+memory and streams.  There is NO fallback: if the shared library is missing, or CUDA is unavailable
+when a compute entry point is called, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import torch
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+_SO = _CSRC / "libmcacq_b200.so"
+
+KERNEL_RBF = 0
+KERNEL_MATERN52 = 1
+TRI_UPPER, TRI_LOWER, TRI_DENSE = 0, 1, 2
+INFO_JITTER_MASK, INFO_NOT_PSD, INFO_NONFINITE = 0x7, 0x8, 0x10
+MAX_Q, MAX_D, MAX_R = 32, 64, 64
+
+_ERRORS = {-1: "MCACQ_EINVAL (bad argument)", -2: "MCACQ_ELIMIT (q/r/d/S outside compiled limits)",
+           -3: "MCACQ_EWORKSPACE (workspace too small)"}
+
+
+class McacqError(RuntimeError):
+    pass
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("d", C.c_int32), ("np", C.c_int32), ("kernel_id", C.c_int32),
+        ("outputscale", C.c_double), ("mean_const", C.c_double), ("y_mean", C.c_double), ("y_std", C.c_double),
+        ("x_offset", C.c_void_p), ("x_coef", C.c_void_p), ("lengthscale", C.c_void_p), ("U_train", C.c_void_p),
+        ("alpha", C.c_void_p), ("R", C.c_void_p), ("Rt", C.c_void_p),
+    ]
+
+
+class Baseline(C.Structure):
+    _fields_ = [("r", C.c_int32), ("_pad", C.c_int32), ("U_base", C.c_void_p), ("A_base", C.c_void_p),
+                ("L_base", C.c_void_p)]
+
+
+class MC(C.Structure):
+    _fields_ = [("S", C.c_int32), ("fat", C.c_int32), ("tau_relu", C.c_double), ("tau_max", C.c_double),
+                ("Zt", C.c_void_p), ("best", C.c_void_p)]
+
+
+def build(force: bool = False) -> Path:
+    """Compile the shared library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", str(_CSRC), "clean"], check=True, capture_output=True)
+    res = subprocess.run(["make", "-C", str(_CSRC), "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise McacqError(f"nvcc build of {_SO.name} failed:\n{res.stdout}\n{res.stderr}")
+    return _SO
+
+
+_lib = None
+
+EXPORTS = [
+    "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
+    "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_acq_forward", "mcacq_acq_backward",
+    "mcacq_last_launch_count",
+]
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library; raises loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _SO.exists():
+        raise McacqError(
+            f"{_SO} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C botorch_b200/csrc`). There is no CPU fallback."
+        )
+    L = C.CDLL(str(_SO))
+    vp, i32, i64, dbl, sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
+    L.mcacq_version.restype = C.c_char_p
+    L.mcacq_num_sms.restype = i32
+    L.mcacq_last_launch_count.restype = i32
+    L.mcacq_scale_inputs.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
+    L.mcacq_cov_cross.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp]
+    L.mcacq_cov_cross_bwd.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp, vp, vp, i32, vp]
+    L.mcacq_dgemm_tri.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
+    L.mcacq_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
+    L.mcacq_workspace_bytes.restype = sz
+    L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]
+    L.mcacq_acq_forward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, sz, vp]
+    L.mcacq_acq_backward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, vp, sz, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("mcacq_version", "mcacq_workspace_bytes"):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise McacqError(f"{what}: {_ERRORS.get(rc, rc)}")
+    raise McacqError(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no GPU'})")
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise McacqError(f"{name} must be a CUDA tensor (got {t.device}); botorch_b200 has no CPU path.")
+    if t.dtype != torch.float64 and t.dtype != torch.int32:
+        raise McacqError(f"{name} must be float64 (got {t.dtype}).")
+    if not t.is_contiguous():
+        raise McacqError(f"{name} must be contiguous.")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m

@@ -1,0 +1,215 @@
+// C-ABI orchestration: workspace carving and the forward / backward / posterior pipelines.
+//
+// Forward  (per call, b q-batches, M = b*q rows):
+//   U   = scale(X)                         scale_inputs_kernel
+//   Kt  = k(U, U_train)            [M x np] cov_cross_kernel
+//   A   = Kt R                     [M x np] dgemm_tri_kernel (upper)          <- dominant FLOPs
+//   mean, Sxx, Sxb                          posterior_blocks_kernel
+//   B, C, acq, info                         sample_reduce_fwd_kernel
+// Backward:
+//   gmean, gSxx, gSxb                       sample_reduce_bwd_kernel
+//   dA (in place over A), row_scale, dU     posterior_blocks_bwd_kernel
+//   dKt = dA R^T    (into the Kt buffer)    dgemm_tri_kernel (lower)          <- dominant FLOPs
+//   dU += sum_k (dKt + s*gmean*alpha) dk/du cov_cross_bwd_kernel
+//   dX  = dU / (coef * lengthscale)         unscale_grad_kernel
+#include "common.cuh"
+
+namespace mcacq {
+
+// defined in blocks.cu / sample_reduce.cu / cov.cu
+int unscale_grad(const double* dU, int64_t rows, int d, const double* coef, const double* ls, double* dX, cudaStream_t st);
+
+}  // namespace mcacq
+
+#include "params.cuh"
+
+namespace mcacq {
+
+int posterior_blocks_fwd(const BlocksParams& p, cudaStream_t st);
+int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st);
+int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
+int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
+
+struct Workspace {
+  double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU;
+  int32_t* counter;
+  size_t bytes;
+};
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static Workspace carve(void* base, int64_t b, int q, int d, int np, int r) {
+  Workspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  const int64_t M = b * q;
+  auto take = [&](size_t nbytes) {
+    char* out = p ? p + off : nullptr;
+    off += al256(nbytes);
+    return out;
+  };
+  w.counter = (int32_t*)take(256);
+  w.U = (double*)take((size_t)M * d * 8);
+  w.Kt = (double*)take((size_t)M * np * 8);
+  w.A = (double*)take((size_t)M * np * 8);
+  w.mean = (double*)take((size_t)M * 8);
+  w.Sxx = (double*)take((size_t)M * q * 8);
+  w.Sxb = (double*)take((size_t)M * (r > 0 ? r : 1) * 8);
+  w.Bm = (double*)take((size_t)M * (r > 0 ? r : 1) * 8);
+  w.Cm = (double*)take((size_t)M * q * 8);
+  w.gmean = (double*)take((size_t)M * 8);
+  w.gSxx = (double*)take((size_t)M * q * 8);
+  w.gSxb = (double*)take((size_t)M * (r > 0 ? r : 1) * 8);
+  w.row_scale = (double*)take((size_t)M * 8);
+  w.dU = (double*)take((size_t)M * d * 8);
+  w.bytes = off;
+  return w;
+}
+
+static int check_model(const mcacq_model* m) {
+  if (!m) return MCACQ_EINVAL;
+  if (m->n <= 0 || m->d <= 0 || m->np < m->n || (m->np % 16) != 0) return MCACQ_EINVAL;
+  if (m->d > MCACQ_MAX_D) return MCACQ_ELIMIT;
+  if (!m->x_offset || !m->x_coef || !m->lengthscale || !m->U_train || !m->alpha || !m->R || !m->Rt) return MCACQ_EINVAL;
+  if (m->kernel_id != MCACQ_KERNEL_RBF && m->kernel_id != MCACQ_KERNEL_MATERN52) return MCACQ_EINVAL;
+  return 0;
+}
+
+// shared front end: U, Kt, A, blocks
+static int run_posterior_stage(const mcacq_model* m, const mcacq_baseline* base, const double* X, int64_t b, int q,
+                               Workspace& w, cudaStream_t st) {
+  const int64_t M = b * q;
+  const int r = base ? base->r : 0;
+  int rc;
+  if ((rc = mcacq_scale_inputs(X, M, m->d, m->x_offset, m->x_coef, m->lengthscale, w.U, st))) return rc;
+  if ((rc = mcacq_cov_cross(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, w.Kt, m->np, st))) return rc;
+  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_UPPER, M, m->np, w.Kt, m->R, w.A, w.counter, st))) return rc;
+  BlocksParams bp;
+  bp.b = b; bp.q = q; bp.d = m->d; bp.np = m->np; bp.r = r;
+  bp.kernel_id = m->kernel_id; bp.outputscale = m->outputscale; bp.mean_const = m->mean_const;
+  bp.y_mean = m->y_mean; bp.y_std = m->y_std;
+  bp.A = w.A; bp.Kt = w.Kt; bp.alpha = m->alpha; bp.U = w.U;
+  bp.A_base = r > 0 ? base->A_base : nullptr;
+  bp.U_base = r > 0 ? base->U_base : nullptr;
+  bp.mean = w.mean; bp.Sxx = w.Sxx; bp.Sxb = w.Sxb;
+  return posterior_blocks_fwd(bp, st);
+}
+
+}  // namespace mcacq
+
+using namespace mcacq;
+
+extern "C" const char* mcacq_version(void) { return "mcacq_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int mcacq_num_sms(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return sms;
+}
+
+extern "C" int mcacq_last_launch_count(void) { return g_launch_count; }
+
+extern "C" size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r) {
+  if (b < 0 || q <= 0 || d <= 0 || np <= 0 || r < 0) return 0;
+  return carve(nullptr, b, q, d, np, r).bytes;
+}
+
+extern "C" int mcacq_posterior(const mcacq_model* model, const double* X, int64_t b, int q, double* mean,
+                               double* covar, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if (!X || !mean || !covar || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
+  if (b == 0) return 0;
+  g_launch_count = 0;
+  Workspace w = carve(workspace, b, q, model->d, model->np, 0);
+  if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
+  // write mean / covariance straight into the caller's buffers
+  w.mean = mean;
+  w.Sxx = covar;
+  return run_posterior_stage(model, nullptr, X, b, q, w, (cudaStream_t)stream);
+}
+
+static int check_mc(const mcacq_mc* mc) {
+  if (!mc || !mc->Zt || !mc->best || mc->S <= 0) return MCACQ_EINVAL;
+  if (!(mc->tau_relu > 0.0) || !(mc->tau_max > 0.0)) return MCACQ_EINVAL;
+  return 0;
+}
+
+static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc, int64_t b, int q, Workspace& w) {
+  const int r = base ? base->r : 0;
+  sp.b = b; sp.q = q; sp.r = r; sp.S = mc->S; sp.fat = mc->fat;
+  sp.tau_relu = mc->tau_relu; sp.tau_max = mc->tau_max;
+  sp.mean = w.mean; sp.Sxx = w.Sxx; sp.Sxb = w.Sxb;
+  sp.L_base = r > 0 ? base->L_base : nullptr;
+  sp.Zt = mc->Zt; sp.best = mc->best;
+  sp.Bm = w.Bm; sp.Cm = w.Cm;
+  sp.acq = nullptr; sp.info = nullptr; sp.grad_acq = nullptr;
+  sp.gmean = w.gmean; sp.gSxx = w.gSxx; sp.gSxb = w.gSxb;
+}
+
+extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc,
+                                 const double* X, int64_t b, int q, double* acq, int32_t* info, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if ((rc = check_mc(mc))) return rc;
+  if (!X || !acq || !info || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
+  const int r = base ? base->r : 0;
+  if (r < 0) return MCACQ_EINVAL;
+  if (r > 0 && (!base->U_base || !base->A_base || !base->L_base)) return MCACQ_EINVAL;
+  if (r > 64) return MCACQ_ELIMIT;
+  if (b == 0) return 0;
+  g_launch_count = 0;
+  Workspace w = carve(workspace, b, q, model->d, model->np, r);
+  if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = run_posterior_stage(model, base, X, b, q, w, st))) return rc;
+  SRParams sp;
+  fill_sr(sp, base, mc, b, q, w);
+  sp.acq = acq; sp.info = info;
+  return sample_reduce_fwd(sp, st);
+}
+
+extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc,
+                                  const double* X, int64_t b, int q, const double* acq, const double* grad_acq,
+                                  double* grad_X, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if ((rc = check_mc(mc))) return rc;
+  if (!X || !acq || !grad_acq || !grad_X || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
+  const int r = base ? base->r : 0;
+  if (r < 0 || r > 64) return r < 0 ? MCACQ_EINVAL : MCACQ_ELIMIT;
+  if (b == 0) return 0;
+  g_launch_count = 0;
+  Workspace w = carve(workspace, b, q, model->d, model->np, r);
+  if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = b * q;
+
+  SRParams sp;
+  fill_sr(sp, base, mc, b, q, w);
+  sp.acq = const_cast<double*>(acq);
+  sp.grad_acq = grad_acq;
+  if ((rc = sample_reduce_bwd(sp, st))) return rc;
+
+  BlocksBwdParams bp;
+  bp.b = b; bp.q = q; bp.d = model->d; bp.np = model->np; bp.r = r;
+  bp.kernel_id = model->kernel_id; bp.outputscale = model->outputscale; bp.y_std = model->y_std;
+  bp.A = w.A;
+  bp.A_base = r > 0 ? base->A_base : nullptr;
+  bp.U = w.U;
+  bp.U_base = r > 0 ? base->U_base : nullptr;
+  bp.gmean = w.gmean; bp.gSxx = w.gSxx; bp.gSxb = w.gSxb;
+  bp.row_scale = w.row_scale; bp.dU = w.dU;
+  if ((rc = posterior_blocks_bwd(bp, st))) return rc;
+
+  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
+  if ((rc = mcacq_cov_cross_bwd(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
+                                model->np, w.row_scale, model->alpha, w.dU, /*accumulate=*/1, st)))
+    return rc;
+  return unscale_grad(w.dU, M, model->d, model->x_coef, model->lengthscale, grad_X, st);
+}

@@ -1,0 +1,297 @@
+// Posterior blocks of a q-batch from the contracted rows A = K(X, X_train) R.
+//
+//   mean[b][i]    = m + s * (c + sum_k Kt[i][k] alpha[k])            gpytorch exact_predictive_mean
+//   Sxx[b][i][j]  = s^2 * (k(u_i, u_j)  - sum_k A[i][k] A[j][k])     gpytorch exact_predictive_covar
+//   Sxb[b][i][j'] = s^2 * (k(u_i, ub_j') - sum_k A[i][k] A_base[j'][k])   (rows -q: of the joint covariance,
+//                                                                     utils/low_rank.py:117-124)
+// followed by Standardize.untransform_posterior (transforms/outcome.py:479-511).
+//
+// Hardware mapping: one warp owns NB consecutive q-batches and sweeps k in steps of 16.  The Gram and
+// cross-Gram tiles are DMMA.8x8x4 contractions whose operands are loaded straight from global memory
+// as 32-byte per-thread vectors: lane (g, t) holds row g, columns k0+4t..k0+4t+3, and the four
+// consecutive DMMA steps use a k-permutation (virtual k = (step, t) <-> actual k0 + 4t + step) that is
+// applied identically to both operands, so no shared-memory staging or shuffles are needed.
+#include "common.cuh"
+#include "params.cuh"
+
+namespace mcacq {
+
+__device__ __forceinline__ void dmma884b(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void load4(const double* p, bool ok, double (&v)[4]) {
+  if (ok) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0.0;
+  }
+}
+
+
+constexpr int BLK_WARPS = 4;
+
+template <int QT, int RT, int NB>
+__global__ void __launch_bounds__(BLK_WARPS * 32)
+posterior_blocks_kernel(BlocksParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t b0 = ((int64_t)blockIdx.x * BLK_WARPS + warp) * NB;
+  if (b0 >= p.b) return;
+  const int q = p.q, np = p.np, r = p.r;
+
+  double accG[NB][QT][QT][2];
+  double accB[NB][QT][RT > 0 ? RT : 1][2];
+  double macc[NB][QT];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      macc[nb][mi] = 0.0;
+#pragma unroll
+      for (int nj = 0; nj < QT; nj++) { accG[nb][mi][nj][0] = 0.0; accG[nb][mi][nj][1] = 0.0; }
+#pragma unroll
+      for (int nj = 0; nj < (RT > 0 ? RT : 1); nj++) { accB[nb][mi][nj][0] = 0.0; accB[nb][mi][nj][1] = 0.0; }
+    }
+
+  for (int k0 = 0; k0 < np; k0 += 16) {
+    const int kc = k0 + 4 * t4;
+    double al[4];
+    load4(p.alpha + kc, true, al);
+    double bf[RT > 0 ? RT : 1][4];
+#pragma unroll
+    for (int nj = 0; nj < RT; nj++) {
+      int row = nj * 8 + g;
+      load4(p.A_base + (int64_t)row * np + kc, row < r, bf[nj]);
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++) {
+      const int64_t bb = b0 + nb;
+      const bool bok = bb < p.b;
+      double af[QT][4];
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        int i = mi * 8 + g;
+        bool ok = bok && i < q;
+        int64_t row = bb * q + i;
+        load4(p.A + row * np + kc, ok, af[mi]);
+        double kf[4];
+        load4(p.Kt + row * np + kc, ok, kf);
+#pragma unroll
+        for (int s = 0; s < 4; s++) macc[nb][mi] = fma(kf[s], al[s], macc[nb][mi]);
+      }
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int mi = 0; mi < QT; mi++) {
+#pragma unroll
+          for (int nj = 0; nj <= mi; nj++) dmma884b(accG[nb][mi][nj][0], accG[nb][mi][nj][1], af[mi][s], af[nj][s]);
+#pragma unroll
+          for (int nj = 0; nj < RT; nj++) dmma884b(accB[nb][mi][nj][0], accB[nb][mi][nj][1], af[mi][s], bf[nj][s]);
+        }
+    }
+  }
+
+  const double s2 = p.y_std * p.y_std;
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    const int64_t bb = b0 + nb;
+    if (bb >= p.b) continue;
+    const double* Ub = p.U + bb * q * p.d;
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      // mean: reduce the 4 lanes of a row group
+      double mv = macc[nb][mi];
+      mv += __shfl_xor_sync(0xffffffffu, mv, 1);
+      mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+      const int i = mi * 8 + g;
+      if (t4 == 0 && i < q) p.mean[bb * q + i] = p.y_mean + p.y_std * (p.mean_const + mv);
+      if (i >= q) continue;
+#pragma unroll
+      for (int nj = 0; nj <= mi; nj++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = nj * 8 + 2 * t4 + e;
+          if (j >= q) continue;
+          double sq = 0.0;
+          for (int k = 0; k < p.d; k++) {
+            double df = Ub[i * p.d + k] - Ub[j * p.d + k];
+            sq = fma(df, df, sq);
+          }
+          double v = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - accG[nb][mi][nj][e]);
+          p.Sxx[(bb * q + i) * q + j] = v;
+          if (nj < mi) p.Sxx[(bb * q + j) * q + i] = v;
+        }
+#pragma unroll
+      for (int nj = 0; nj < RT; nj++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = nj * 8 + 2 * t4 + e;
+          if (j >= r) continue;
+          double sq = 0.0;
+          for (int k = 0; k < p.d; k++) {
+            double df = Ub[i * p.d + k] - p.U_base[j * p.d + k];
+            sq = fma(df, df, sq);
+          }
+          p.Sxb[(bb * q + i) * r + j] = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - accB[nb][mi][nj][e]);
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward:  dA[i][:] = -s^2 * ( sum_j (gSxx[i][j] + gSxx[j][i]) A[j][:] + sum_j' gSxb[i][j'] A_base[j'][:] )
+// written IN PLACE over A, row_scale[i] = s * gmean[i] (the rank-1 mean term is applied by the covariance
+// backward kernel), and the direct kernel terms of K(X, X) and K(X, X_base) into dU.
+
+template <int QT, int RT>
+__global__ void __launch_bounds__(BLK_WARPS * 32)
+posterior_blocks_bwd_kernel(BlocksBwdParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t bb = (int64_t)blockIdx.x * BLK_WARPS + warp;
+  if (bb >= p.b) return;
+  const int q = p.q, np = p.np, r = p.r, d = p.d;
+  const double s2 = p.y_std * p.y_std;
+  const double* gxx = p.gSxx + bb * q * q;
+  const double* gxb = p.gSxb + bb * q * r;
+
+  // coefficient fragments (A operand): row i = 8*mi + g, contracted index = 4*kk + t4
+  double cq[QT][2 * QT];
+  double cb[QT][RT > 0 ? 2 * RT : 1];
+#pragma unroll
+  for (int mi = 0; mi < QT; mi++) {
+    const int i = mi * 8 + g;
+#pragma unroll
+    for (int kk = 0; kk < 2 * QT; kk++) {
+      const int j = kk * 4 + t4;
+      cq[mi][kk] = (i < q && j < q) ? -s2 * (gxx[i * q + j] + gxx[j * q + i]) : 0.0;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2 * RT; kk++) {
+      const int j = kk * 4 + t4;
+      cb[mi][kk] = (i < q && j < r) ? -s2 * gxb[i * r + j] : 0.0;
+    }
+  }
+
+  double* Ab = p.A + bb * q * np;
+  for (int c0 = 0; c0 < np; c0 += 16) {
+    const int cc = c0 + 2 * g;  // this lane's two source columns
+    double acc[QT][2][2];
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) { acc[mi][0][0] = acc[mi][0][1] = acc[mi][1][0] = acc[mi][1][1] = 0.0; }
+    double2 rq[2 * QT];
+#pragma unroll
+    for (int kk = 0; kk < 2 * QT; kk++) {
+      const int j = kk * 4 + t4;
+      rq[kk] = (j < q) ? *reinterpret_cast<const double2*>(Ab + (int64_t)j * np + cc) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2 * RT; kk++) {
+      const int j = kk * 4 + t4;
+      double2 rb = (j < r) ? *reinterpret_cast<const double2*>(p.A_base + (int64_t)j * np + cc) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        dmma884b(acc[mi][0][0], acc[mi][0][1], cb[mi][kk], rb.x);
+        dmma884b(acc[mi][1][0], acc[mi][1][1], cb[mi][kk], rb.y);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2 * QT; kk++)
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        dmma884b(acc[mi][0][0], acc[mi][0][1], cq[mi][kk], rq[kk].x);
+        dmma884b(acc[mi][1][0], acc[mi][1][1], cq[mi][kk], rq[kk].y);
+      }
+    // tile0 column n <-> actual c0 + 2n, tile1 <-> c0 + 2n + 1: lane holds actual columns c0+4*t4 .. +3
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      const int i = mi * 8 + g;
+      if (i < q) {
+        double* dst = Ab + (int64_t)i * np + c0 + 4 * t4;
+        *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][0][0], acc[mi][1][0]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[mi][0][1], acc[mi][1][1]);
+      }
+    }
+  }
+
+  // rank-1 mean term scale and direct kernel terms
+  const double* Ub = p.U + bb * q * d;
+  for (int idx = lane; idx < q; idx += 32) p.row_scale[bb * q + idx] = p.y_std * p.gmean[bb * q + idx];
+  for (int idx = lane; idx < q * d; idx += 32) {
+    const int i = idx / d, k = idx - i * d;
+    double accu = 0.0;
+    for (int j = 0; j < q; j++) {
+      if (j == i) continue;
+      double sq = 0.0;
+      for (int kk = 0; kk < d; kk++) {
+        double df = Ub[i * d + kk] - Ub[j * d + kk];
+        sq = fma(df, df, sq);
+      }
+      double w = s2 * (gxx[i * q + j] + gxx[j * q + i]) * kernel_dfactor(p.kernel_id, p.outputscale, sq);
+      accu = fma(w, Ub[i * d + k] - Ub[j * d + k], accu);
+    }
+    for (int j = 0; j < r; j++) {
+      double sq = 0.0;
+      for (int kk = 0; kk < d; kk++) {
+        double df = Ub[i * d + kk] - p.U_base[j * d + kk];
+        sq = fma(df, df, sq);
+      }
+      double w = s2 * gxb[i * r + j] * kernel_dfactor(p.kernel_id, p.outputscale, sq);
+      accu = fma(w, Ub[i * d + k] - p.U_base[j * d + k], accu);
+    }
+    p.dU[(bb * q + i) * d + k] = accu;
+  }
+}
+
+template <int QT, int RT>
+static int launch_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
+  constexpr int NB = (QT == 1 && RT <= 4) ? 4 : 1;
+  int64_t per_cta = (int64_t)BLK_WARPS * NB;
+  int64_t blocks = (p.b + per_cta - 1) / per_cta;
+  posterior_blocks_kernel<QT, RT, NB><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int QT, int RT>
+static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
+  int64_t blocks = (p.b + BLK_WARPS - 1) / BLK_WARPS;
+  posterior_blocks_bwd_kernel<QT, RT><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+#define MCACQ_DISPATCH_QT_RT(FN, p, st)                                   \
+  do {                                                                    \
+    const int qt_ = (p.q + 7) / 8, rt_ = (p.r + 7) / 8;                   \
+    if (qt_ == 1) {                                                       \
+      if (rt_ == 0) return FN<1, 0>(p, st);                               \
+      if (rt_ == 1) return FN<1, 1>(p, st);                               \
+      if (rt_ == 2) return FN<1, 2>(p, st);                               \
+      if (rt_ <= 4) return FN<1, 4>(p, st);                               \
+      if (rt_ <= 8) return FN<1, 8>(p, st);                               \
+    } else if (qt_ == 2) {                                                \
+      if (rt_ == 0) return FN<2, 0>(p, st);                               \
+      if (rt_ <= 2) return FN<2, 2>(p, st);                               \
+      if (rt_ <= 4) return FN<2, 4>(p, st);                               \
+      if (rt_ <= 8) return FN<2, 8>(p, st);                               \
+    } else if (qt_ <= 4) {                                                \
+      if (rt_ == 0) return FN<4, 0>(p, st);                               \
+      if (rt_ <= 4) return FN<4, 4>(p, st);                               \
+      if (rt_ <= 8) return FN<4, 8>(p, st);                               \
+    }                                                                     \
+    return MCACQ_ELIMIT;                                                  \
+  } while (0)
+
+int posterior_blocks_fwd(const BlocksParams& p, cudaStream_t st) { MCACQ_DISPATCH_QT_RT(launch_blocks_fwd, p, st); }
+int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) { MCACQ_DISPATCH_QT_RT(launch_blocks_bwd, p, st); }
+
+}  // namespace mcacq

@@ -1,0 +1,58 @@
+// Parameter blocks shared by the stage kernels and the C-ABI orchestration.
+#pragma once
+#include <stdint.h>
+namespace mcacq {
+struct BlocksParams {
+  int64_t b;
+  int q, d, np, r;
+  int kernel_id;
+  double outputscale, mean_const, y_mean, y_std;
+  const double* A;      // [b*q x np]
+  const double* Kt;     // [b*q x np]
+  const double* alpha;  // [np]
+  const double* U;      // [b*q x d]
+  const double* A_base; // [r x np]
+  const double* U_base; // [r x d]
+  double* mean;         // [b*q]
+  double* Sxx;          // [b x q x q]
+  double* Sxb;          // [b x q x r]
+};
+
+struct BlocksBwdParams {
+  int64_t b;
+  int q, d, np, r;
+  int kernel_id;
+  double outputscale, y_std;
+  double* A;              // [b*q x np]  in: A, out: dA
+  const double* A_base;   // [r x np]
+  const double* U;        // [b*q x d]
+  const double* U_base;   // [r x d]
+  const double* gmean;    // [b*q]
+  const double* gSxx;     // [b x q x q]
+  const double* gSxb;     // [b x q x r]
+  double* row_scale;      // [b*q]
+  double* dU;             // [b*q x d]
+};
+
+struct SRParams {
+  int64_t b;
+  int q, r, S, fat;
+  double tau_relu, tau_max;
+  const double* mean;    // [b*q]
+  const double* Sxx;     // [b x q x q]
+  const double* Sxb;     // [b x q x r]
+  const double* L_base;  // [r x r]
+  const double* Zt;      // [(r+q) x S]
+  const double* best;    // [S]
+  double* Bm;            // [b x q x r]
+  double* Cm;            // [b x q x q]
+  double* acq;           // [b]
+  int32_t* info;         // [b]
+  // backward only
+  const double* grad_acq;  // [b]
+  double* gmean;           // [b*q]
+  double* gSxx;            // [b x q x q]
+  double* gSxb;            // [b x q x r]
+};
+
+}  // namespace mcacq

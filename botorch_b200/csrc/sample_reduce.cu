@@ -1,0 +1,532 @@
+// Fused reparameterised-sample / utility / reduction kernels (forward and hand-written backward).
+//
+// Per q-batch (one CTA):
+//   B  = Sxb L_base^{-T}                         torch.linalg.solve_triangular in sample_cached_cholesky
+//                                                (botorch/utils/low_rank.py:130-132)
+//   C  = psd_safe_cholesky(Sxx - B B^T, 6)       (low_rank.py:137-140; jitter 1e-8*10^i on failure)
+//   y[s][i] = mean[i] + sum_j B[i][j] Z[s][j] + sum_{j<=i} C[i][j] Z[s][r+j]      (low_rank.py:143-160)
+//   li = log_fatplus(y - best[s], tau_relu)      (botorch/acquisition/logei.py:688-715, safe_math.py:298-325)
+//   fm[s] = fatmax_i(li, tau_max)                (safe_math.py:328-355, _inf_max_helper :146-191)
+//   acq = logsumexp_s fm[s] - log S              (safe_math.py:213-225)
+// r == 0 gives the qLogEI path (posteriors/gpytorch.py:86-127: y = mean + chol(Sxx) z).
+// The backward kernel recomputes the per-sample chain, forms the softmax/fatmax/log_fatplus weights
+// (same weights as botorch/csrc/logei_fused.cpp:109-111, 143-174), contracts them with
+// the base samples, and runs the q x q Cholesky reverse-mode and the triangular-solve reverse-mode in
+// shared memory.
+#include "common.cuh"
+#include "params.cuh"
+#include <math_constants.h>
+
+namespace mcacq {
+
+
+constexpr int SR_THREADS = 256;
+constexpr int SR_WARPS = SR_THREADS / 32;
+
+// ---- utility pieces -----------------------------------------------------------------------------
+// log-improvement value and derivative w.r.t. z (the improvement y - best).
+template <bool GRAD>
+__device__ __forceinline__ double log_improve(double z, double tau, int fat, double& dli) {
+  if (fat) {
+    const double u = z / tau;
+    double sp, dsp;
+    if (u > 20.0) {  // torch softplus threshold
+      sp = u; dsp = 1.0;
+    } else if (u < -746.0) {  // exp(u) == 0 exactly in fp64
+      sp = 0.0; dsp = 0.0;
+    } else {
+      const double e = exp(u);
+      sp = log1p(e);
+      dsp = e / (e + 1.0);
+    }
+    const double den = 1.0 + u * u;
+    const double ca = 1.0 / den;
+    const double f = sp + 0.1 * ca;
+    if (GRAD) dli = (dsp - 0.2 * u * ca * ca) / (tau * f);
+    return log(tau * f);
+  } else {
+    const double xt = z / tau;
+    if (xt > -35.0) {
+      const double beta = 1.0 / tau;
+      const double xb = z * beta;
+      double sp, dsp;
+      if (xb > 32.0) { sp = z; dsp = 1.0; }
+      else { const double e = exp(xb); sp = log1p(e) / beta; dsp = e / (e + 1.0); }
+      if (GRAD) dli = dsp / sp;
+      return log(sp);
+    } else {
+      if (GRAD) dli = 1.0 / tau;
+      return xt + log(tau);
+    }
+  }
+}
+
+// q-reduction: fatmax (fat) or smooth_amax; optionally the weights d fm / d li_i.
+template <int QMAX, bool GRAD>
+__device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, double tau, int fat, double (&w)[QMAX]) {
+  double M = -CUDART_INF;
+#pragma unroll
+  for (int i = 0; i < QMAX; i++) if (i < q) M = fmax(M, li[i]);
+  if (isinf(M) || isnan(M)) {
+    // _inf_max_helper: the result is the sum of the infinite maxima; gradient 1 on those entries
+    double res = 0.0;
+#pragma unroll
+    for (int i = 0; i < QMAX; i++) if (i < q) {
+      bool is_max = (li[i] == M);
+      if (is_max) res += li[i];
+      if (GRAD) w[i] = is_max ? 1.0 : 0.0;
+    }
+    return isnan(M) ? M : res;
+  }
+  if (fat) {
+    double P = 0.0, dsum = 0.0;
+    int cnt = 0;
+    double dp[QMAX];
+#pragma unroll
+    for (int i = 0; i < QMAX; i++) if (i < q) {
+      const double v = (M - li[i]) / tau;
+      const double den = 2.0 + 2.0 * v + v * v;
+      P += 2.0 / den;
+      if (GRAD) {
+        dp[i] = -(4.0 + 4.0 * v) / (den * den);
+        dsum += dp[i];
+        cnt += (li[i] == M) ? 1 : 0;
+      }
+    }
+    if (GRAD) {
+      const double head = (1.0 + dsum / P) / (double)cnt;
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) if (i < q) w[i] = ((li[i] == M) ? head : 0.0) - dp[i] / P;
+    }
+    return M + tau * log(P);
+  } else {
+    const double Mt = M / tau;
+    double ssum = 0.0;
+#pragma unroll
+    for (int i = 0; i < QMAX; i++) if (i < q) {
+      const double e = exp(li[i] / tau - Mt);
+      ssum += e;
+      if (GRAD) w[i] = e;
+    }
+    if (GRAD) {
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) if (i < q) w[i] /= ssum;
+    }
+    return (Mt + log(ssum)) * tau;
+  }
+}
+
+__device__ __forceinline__ void lse_push(double& m, double& s, double f) {
+  if (f == -CUDART_INF) return;
+  if (f > m) { s = s * exp(m - f) + 1.0; m = f; }
+  else s += exp(f - m);
+}
+__device__ __forceinline__ void lse_merge(double& m, double& s, double m2, double s2) {
+  const double M = fmax(m, m2);
+  if (M == -CUDART_INF) { m = M; s = 0.0; return; }
+  if (isinf(M)) { m = M; s = 1.0; return; }
+  const double a = (m == -CUDART_INF) ? 0.0 : s * exp(m - M);
+  const double c = (m2 == -CUDART_INF) ? 0.0 : s2 * exp(m2 - M);
+  m = M; s = a + c;
+}
+
+// ---- shared prologue: load factors into shared memory -------------------------------------------
+// coefT[j][i] (j < r: B[i][j]; j >= r: C[i][j-r]), row pitch QP = q rounded up to even.
+__device__ __forceinline__ int coef_pitch(int q) { return (q + 1) & ~1; }
+
+// Forward -------------------------------------------------------------------------------------------
+template <int QMAX, int NS>
+__global__ void __launch_bounds__(SR_THREADS)
+sample_reduce_fwd_kernel(SRParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int q = p.q, r = p.r, S = p.S;
+  const int QP = coef_pitch(q);
+  double* coefT = sm;                          // [(r+q)][QP]
+  double* brow = coefT + (size_t)(r + q) * QP; // [q][r]   row-major scratch for the triangular solve
+  double* Tm = brow + (size_t)q * r;           // [q][q]
+  double* smean = Tm + q * q;                  // [q]
+  double* red = smean + q;                     // [2 * SR_WARPS]
+  __shared__ int s_info;
+  __shared__ int s_nonfinite;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t bb = blockIdx.x;
+
+  for (int idx = tid; idx < q * r; idx += SR_THREADS) brow[idx] = p.Sxb[bb * q * r + idx];
+  for (int idx = tid; idx < q; idx += SR_THREADS) smean[idx] = p.mean[bb * q + idx];
+  for (int idx = tid; idx < (r + q) * QP; idx += SR_THREADS) coefT[idx] = 0.0;
+  if (tid == 0) { s_info = 0; s_nonfinite = 0; }
+  __syncthreads();
+
+  // ---- B = Sxb L^{-T}: forward substitution, one warp per row, lanes over the dot product
+  for (int i = warp; i < q; i += SR_WARPS) {
+    double* bi = brow + (size_t)i * r;
+    for (int j = 0; j < r; j++) {
+      const double* Lj = p.L_base + (size_t)j * r;
+      double part = 0.0;
+      for (int k = lane; k < j; k += 32) part = fma(bi[k], Lj[k], part);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) bi[j] = (bi[j] - part) / Lj[j];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+    const int i = idx / r, j = idx - i * r;
+    const double v = brow[idx];
+    coefT[j * QP + i] = v;
+    p.Bm[bb * q * r + idx] = v;
+  }
+  // ---- T = Sxx - B B^T (lower triangle)
+  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+    const int i = idx / q, j = idx - i * q;
+    double v = 0.0;
+    if (j <= i) {
+      double dot = 0.0;
+      for (int k = 0; k < r; k++) dot = fma(brow[i * r + k], brow[j * r + k], dot);
+      v = p.Sxx[bb * q * q + idx] - dot;
+    }
+    Tm[idx] = v;
+  }
+  __syncthreads();
+
+  // ---- C = psd_safe_cholesky(T): warp 0, lane = row; up to 6 jitter escalations
+  if (warp == 0) {
+    double* Cs = brow;  // reuse scratch (q*q <= needs q*max(r,q); sized on host)
+    double jit_prev = 0.0;
+    double diag = (lane < q) ? Tm[lane * q + lane] : 1.0;
+    int info = 0;
+    bool ok = false;
+    for (int attempt = 0; attempt <= 6; attempt++) {
+      if (attempt > 0) {
+        // linear_operator psd_safe_cholesky: jitter_new = 1e-8 * (10 ** i), i = attempt - 1
+        const double p10[6] = {1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0};
+        const double jit_new = 1e-8 * p10[attempt - 1];
+        diag += (jit_new - jit_prev);
+        jit_prev = jit_new;
+        info = attempt;
+      }
+      ok = true;
+      for (int j = 0; j < q; j++) {
+        double v = 0.0;
+        if (lane >= j && lane < q) {
+          v = (lane == j) ? diag : Tm[lane * q + j];
+          for (int k = 0; k < j; k++) v -= Cs[lane * q + k] * Cs[j * q + k];
+        }
+        const double dj = __shfl_sync(0xffffffffu, v, j);
+        if (!(dj > 0.0)) { ok = false; break; }
+        const double sj = sqrt(dj);
+        if (lane >= j && lane < q) Cs[lane * q + j] = (lane == j) ? sj : v / sj;
+        __syncwarp();
+      }
+      if (ok) break;
+    }
+    if (!ok) info = 6 | MCACQ_INFO_NOT_PSD;
+    if (lane < q) {
+      for (int j = 0; j < q; j++) {
+        double v = (j <= lane) ? (ok ? Cs[lane * q + j] : CUDART_NAN) : 0.0;
+        coefT[(r + j) * QP + lane] = v;
+        p.Cm[bb * q * q + lane * q + j] = v;
+      }
+    }
+    if (lane == 0) s_info = info;
+  }
+  __syncthreads();
+
+  // ---- samples: NS samples per thread, coefficients broadcast from shared memory
+  double lm = -CUDART_INF, ls = 0.0;
+  bool nonfinite = false;
+  for (int s0 = tid * NS; s0 < S; s0 += SR_THREADS * NS) {
+    double y[NS][QMAX];
+#pragma unroll
+    for (int ns = 0; ns < NS; ns++)
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+    for (int j = 0; j < r + q; j++) {
+      double z[NS];
+#pragma unroll
+      for (int ns = 0; ns < NS; ns++) z[ns] = (s0 + ns < S) ? p.Zt[(size_t)j * S + s0 + ns] : 0.0;
+      const double* cj = coefT + j * QP;
+#pragma unroll
+      for (int i = 0; i < QMAX; i += 2) {
+        if (i < q) {
+          const double2 c2 = *reinterpret_cast<const double2*>(cj + i);
+#pragma unroll
+          for (int ns = 0; ns < NS; ns++) {
+            y[ns][i] = fma(c2.x, z[ns], y[ns][i]);
+            if (i + 1 < QMAX) y[ns][i + 1] = fma(c2.y, z[ns], y[ns][i + 1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ns = 0; ns < NS; ns++) {
+      if (s0 + ns < S) {
+        const double bst = p.best[s0 + ns];
+        double li[QMAX], wdummy[QMAX];
+#pragma unroll
+        for (int i = 0; i < QMAX; i++) {
+          if (i < q) {
+            const double yi = y[ns][i] + smean[i];
+            if (!isfinite(yi)) nonfinite = true;
+            double dl;
+            li[i] = log_improve<false>(yi - bst, p.tau_relu, p.fat, dl);
+          } else li[i] = -CUDART_INF;
+        }
+        const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, p.fat, wdummy);
+        if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
+        else lse_push(lm, ls, fm);
+      }
+    }
+  }
+  if (nonfinite) s_nonfinite = 1;
+  // ---- CTA logsumexp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double m2 = __shfl_xor_sync(0xffffffffu, lm, o);
+    const double s2 = __shfl_xor_sync(0xffffffffu, ls, o);
+    lse_merge(lm, ls, m2, s2);
+  }
+  if (lane == 0) { red[2 * warp] = lm; red[2 * warp + 1] = ls; }
+  __syncthreads();
+  if (tid == 0) {
+    double m = red[0], s = red[1];
+    for (int w = 1; w < SR_WARPS; w++) lse_merge(m, s, red[2 * w], red[2 * w + 1]);
+    double res;
+    if (S == 0 || m == -CUDART_INF) res = -CUDART_INF;
+    else if (isinf(m)) res = m;
+    else res = m + log(s) - log((double)S);
+    if (s_info & MCACQ_INFO_NOT_PSD) res = CUDART_NAN;
+    p.acq[bb] = res;
+    p.info[bb] = s_info | (s_nonfinite ? MCACQ_INFO_NONFINITE : 0);
+  }
+}
+
+// Backward ------------------------------------------------------------------------------------------
+template <int QMAX, int NS>
+__global__ void __launch_bounds__(SR_THREADS)
+sample_reduce_bwd_kernel(SRParams p, int chunk) {
+  extern __shared__ __align__(16) double sm[];
+  const int q = p.q, r = p.r, S = p.S;
+  const int QP = coef_pitch(q);
+  const int NC = r + q + 1;                    // contraction outputs per row: B (r), C (q), mean (1)
+  double* coefT = sm;                          // [(r+q)][QP]
+  double* gco = coefT + (size_t)(r + q) * QP;  // [q][NC]  accumulated d/d[B C mean]
+  double* smean = gco + (size_t)q * NC;        // [q]
+  double* mats = smean + q;                    // 4 x [q][q] scratch: L, P/X, G, gT
+  double* gy = mats + 4 * q * q;               // [chunk][q]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t bb = blockIdx.x;
+
+  for (int idx = tid; idx < (r + q) * QP; idx += SR_THREADS) coefT[idx] = 0.0;
+  for (int idx = tid; idx < q * NC; idx += SR_THREADS) gco[idx] = 0.0;
+  for (int idx = tid; idx < q; idx += SR_THREADS) smean[idx] = p.mean[bb * q + idx];
+  __syncthreads();
+  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+    const int i = idx / r, j = idx - i * r;
+    coefT[j * QP + i] = p.Bm[bb * q * r + idx];
+  }
+  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+    const int i = idx / q, j = idx - i * q;
+    coefT[(r + j) * QP + i] = p.Cm[bb * q * q + idx];
+  }
+  __syncthreads();
+
+  const double gout = p.grad_acq[bb];
+  const double lse_total = p.acq[bb] + log((double)S);
+
+  const int n_out = q * NC;
+
+  for (int c0 = 0; c0 < S; c0 += chunk) {
+    const int cend = (c0 + chunk < S) ? c0 + chunk : S;
+    // ---- pass A: per-sample weights gy[s][i]
+    for (int s0 = c0 + tid * NS; s0 < cend; s0 += SR_THREADS * NS) {
+      double y[NS][QMAX];
+#pragma unroll
+      for (int ns = 0; ns < NS; ns++)
+#pragma unroll
+        for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+      for (int j = 0; j < r + q; j++) {
+        double z[NS];
+#pragma unroll
+        for (int ns = 0; ns < NS; ns++) z[ns] = (s0 + ns < cend) ? p.Zt[(size_t)j * S + s0 + ns] : 0.0;
+        const double* cj = coefT + j * QP;
+#pragma unroll
+        for (int i = 0; i < QMAX; i += 2) {
+          if (i < q) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cj + i);
+#pragma unroll
+            for (int ns = 0; ns < NS; ns++) {
+              y[ns][i] = fma(c2.x, z[ns], y[ns][i]);
+              if (i + 1 < QMAX) y[ns][i + 1] = fma(c2.y, z[ns], y[ns][i + 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int ns = 0; ns < NS; ns++) {
+        if (s0 + ns < cend) {
+          const double bst = p.best[s0 + ns];
+          double li[QMAX], dli[QMAX], w[QMAX];
+#pragma unroll
+          for (int i = 0; i < QMAX; i++) {
+            if (i < q) li[i] = log_improve<true>(y[ns][i] + smean[i] - bst, p.tau_relu, p.fat, dli[i]);
+            else { li[i] = -CUDART_INF; dli[i] = 0.0; }
+          }
+          const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, p.fat, w);
+          double ws;
+          if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
+          else ws = gout * exp(fm - lse_total);
+          double* gys = gy + (size_t)(s0 + ns - c0) * q;
+#pragma unroll
+          for (int i = 0; i < QMAX; i++) if (i < q) gys[i] = ws * w[i] * dli[i];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass B: gco[i][j] += sum_s gy[s][i] * Z[s][j]   (j == r+q: the mean column, Z == 1)
+    for (int o = tid; o < n_out; o += SR_THREADS) {
+      const int j = o / q, i = o - j * q;  // i fastest: lanes of a warp share few j rows
+      double a = 0.0;
+      if (j < r + q) {
+        const double* zr = p.Zt + (size_t)j * S + c0;
+        for (int s = 0; s < cend - c0; s++) a = fma(gy[(size_t)s * q + i], zr[s], a);
+      } else {
+        for (int s = 0; s < cend - c0; s++) a += gy[(size_t)s * q + i];
+      }
+      gco[i * NC + j] += a;  // each (i, j) is owned by exactly one thread
+    }
+    __syncthreads();
+  }
+
+  // ---- Cholesky reverse-mode (warp 0): gT = sym( L^{-T} Phi(L^T gL) L^{-1} )
+  double* Lm = mats;
+  double* Xm = mats + q * q;
+  double* Gm = mats + 2 * q * q;
+  double* gT = mats + 3 * q * q;
+  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+    const int i = idx / q, j = idx - i * q;
+    Lm[idx] = (j <= i) ? coefT[(r + j) * QP + i] : 0.0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // P = Phi(L^T gL), lane = column c
+    if (lane < q) {
+      const int c = lane;
+      for (int a = 0; a < q; a++) {
+        double v = 0.0;
+        if (a >= c) {
+          for (int k = a; k < q; k++) v = fma(Lm[k * q + a], gco[k * NC + r + c], v);  // gL[k][c], k >= a >= c
+          if (a == c) v *= 0.5;
+        }
+        Xm[a * q + c] = v;
+      }
+      // X = L^{-T} P (back substitution down the rows), column c independent
+      for (int a = q - 1; a >= 0; a--) {
+        double v = Xm[a * q + c];
+        for (int k = a + 1; k < q; k++) v -= Lm[k * q + a] * Xm[k * q + c];
+        Xm[a * q + c] = v / Lm[a * q + a];
+      }
+    }
+    __syncwarp();
+    // G = X L^{-1}: lane = row a
+    if (lane < q) {
+      const int a = lane;
+      for (int c = q - 1; c >= 0; c--) {
+        double v = Xm[a * q + c];
+        for (int k = c + 1; k < q; k++) v -= Gm[a * q + k] * Lm[k * q + c];
+        Gm[a * q + c] = v / Lm[c * q + c];
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < q * q; idx += 32) {
+      const int i = idx / q, j = idx - i * q;
+      gT[idx] = 0.5 * (Gm[i * q + j] + Gm[j * q + i]);
+    }
+  }
+  __syncthreads();
+  // ---- outputs: gmean, gSxx = gT, gB_tot = gB - 2 gT B
+  for (int idx = tid; idx < q; idx += SR_THREADS) p.gmean[bb * q + idx] = gco[idx * NC + r + q];
+  for (int idx = tid; idx < q * q; idx += SR_THREADS) p.gSxx[bb * q * q + idx] = gT[idx];
+  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+    const int i = idx / r, j = idx - i * r;
+    double v = gco[i * NC + j];
+    for (int k = 0; k < q; k++) v -= 2.0 * gT[i * q + k] * coefT[j * QP + k];
+    gy[idx] = v;  // reuse gy scratch as gB_tot [q][r]  (chunk*q >= q*r guaranteed by the host)
+  }
+  __syncthreads();
+  // ---- gSxb = gB_tot L_base^{-1}: backward substitution, one warp per row
+  for (int i = warp; i < q; i += SR_WARPS) {
+    double* gi = gy + (size_t)i * r;
+    for (int j = r - 1; j >= 0; j--) {
+      double part = 0.0;
+      for (int k = j + 1 + lane; k < r; k += 32) part = fma(gi[k], p.L_base[(size_t)k * r + j], part);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) gi[j] = (gi[j] - part) / p.L_base[(size_t)j * r + j];
+      __syncwarp();
+    }
+    for (int j = lane; j < r; j += 32) p.gSxb[(bb * q + i) * r + j] = gi[j];
+  }
+}
+
+// ---- host launchers --------------------------------------------------------------------------------
+static size_t fwd_smem(int q, int r) {
+  int QP = (q + 1) & ~1;
+  size_t scratch = (size_t)q * (r > q ? r : q);
+  return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS) * sizeof(double);
+}
+
+static size_t bwd_smem(int q, int r, int chunk) {
+  int QP = (q + 1) & ~1;
+  return ((size_t)(r + q) * QP + (size_t)q * (r + q + 1) + q + 4 * (size_t)q * q + (size_t)chunk * q) * sizeof(double);
+}
+
+template <int QMAX, int NS>
+static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
+  size_t smem = fwd_smem(p.q, p.r);
+  if (smem > 200 * 1024) return MCACQ_ELIMIT;
+  auto kern = sample_reduce_fwd_kernel<QMAX, NS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)p.b, SR_THREADS, smem, st>>>(p);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int QMAX, int NS>
+static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
+  // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
+  int chunk = (64 * 1024) / (8 * p.q);
+  if (chunk > p.S) chunk = p.S;
+  chunk = (chunk / (SR_THREADS * NS)) * (SR_THREADS * NS);
+  if (chunk < SR_THREADS * NS) chunk = SR_THREADS * NS;
+  if (chunk < p.r) chunk = p.r;
+  size_t smem = bwd_smem(p.q, p.r, chunk);
+  if (smem > 200 * 1024) return MCACQ_ELIMIT;
+  auto kern = sample_reduce_bwd_kernel<QMAX, NS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)p.b, SR_THREADS, smem, st>>>(p, chunk);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int sample_reduce_fwd(const SRParams& p, cudaStream_t st) {
+  if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
+  if (p.b == 0) return 0;
+  if (p.q <= 8) return launch_sr_fwd<8, 4>(p, st);
+  if (p.q <= 16) return launch_sr_fwd<16, 2>(p, st);
+  return launch_sr_fwd<32, 1>(p, st);
+}
+
+int sample_reduce_bwd(const SRParams& p, cudaStream_t st) {
+  if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
+  if (p.b == 0) return 0;
+  if (p.q <= 8) return launch_sr_bwd<8, 4>(p, st);
+  if (p.q <= 16) return launch_sr_bwd<16, 2>(p, st);
+  return launch_sr_bwd<32, 1>(p, st);
+}
+
+}  // namespace mcacq

@@ -1,0 +1,151 @@
+"""Device-resident exact-GP prediction caches and the C-ABI model descriptor.
+
+B200-native counterpart of gpytorch's `DefaultPredictionStrategy` as BoTorch configures it
+(botorch/__init__.py:52-57, botorch/models/utils/assorted.py:305-315): the train Cholesky factor `L`,
+`mean_cache = (K + noise)^{-1} (y - c)` and `covar_cache = L^{-T}` are built once per fitted model
+ and stay resident in HBM; every posterior / acquisition call then only
+runs the hand-written kernels of `csrc/`.  The one-off factorisation uses torch's cuSOLVER Cholesky and
+triangular solve (a plain library call on an n x n matrix, off the per-evaluation path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from ..exceptions.errors import NanError, NotPSDError
+from ..exceptions.warnings import NumericalWarning
+
+
+def psd_safe_cholesky(A: Tensor, max_tries: int = 6, jitter: float | None = None) -> Tensor:
+    """`linear_operator.utils.cholesky.psd_safe_cholesky` semantics (jitter only on failing batch
+    elements, 1e-8 * 10^i in fp64), evaluated with torch on the tensor's device."""
+    L, info = torch.linalg.cholesky_ex(A)
+    if not torch.any(info):
+        return L
+    if torch.isnan(A).any():
+        raise NanError(f"cholesky: {int(torch.isnan(A).sum())} of {A.numel()} elements are NaN.")
+    if jitter is None:
+        jitter = 1e-6 if A.dtype == torch.float32 else 1e-8
+    Aprime = A.clone()
+    jitter_prev = 0.0
+    for i in range(max_tries):
+        jitter_new = jitter * (10**i)
+        diag_add = ((info > 0) * (jitter_new - jitter_prev)).unsqueeze(-1).expand(*Aprime.shape[:-1])
+        Aprime.diagonal(dim1=-1, dim2=-2).add_(diag_add)
+        jitter_prev = jitter_new
+        warnings.warn(f"A not p.d., added jitter of {jitter_new:.1e} to the diagonal", NumericalWarning)
+        L, info = torch.linalg.cholesky_ex(Aprime)
+        if not torch.any(info):
+            return L
+    raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {jitter_new:.1e}.")
+
+
+class DevicePredictionStrategy:
+    """Holds the fitted-state operands of `mcacq_model` on one CUDA device."""
+
+    def __init__(
+        self,
+        train_X_transformed: Tensor,  # n x d, already through the input transform
+        train_Y_standardized: Tensor,  # n (standardised targets)
+        lengthscale: Tensor,  # d
+        noise: Tensor,  # scalar or n
+        kernel_id: int,
+        outputscale: float,
+        mean_const: float,
+        x_offset: Tensor,  # d
+        x_coef: Tensor,  # d
+        y_mean: float,
+        y_std: float,
+    ) -> None:
+        dev = train_X_transformed.device
+        if dev.type != "cuda":
+            raise _lib.McacqError("DevicePredictionStrategy requires CUDA tensors; botorch_b200 has no CPU path.")
+        f64 = dict(device=dev, dtype=torch.float64)
+        self.device = dev
+        self.n, self.d = train_X_transformed.shape
+        self.np = _lib.round_up(self.n, 16)
+        self.kernel_id, self.outputscale, self.mean_const = kernel_id, float(outputscale), float(mean_const)
+        self.y_mean, self.y_std = float(y_mean), float(y_std)
+        self.x_offset = x_offset.to(**f64).contiguous()
+        self.x_coef = x_coef.to(**f64).contiguous()
+        self.lengthscale = lengthscale.to(**f64).reshape(-1).contiguous()
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        n, d, npad = self.n, self.d, self.np
+        # scaled train inputs: the train inputs are already input-transformed, so only divide by l
+        zeros, ones = torch.zeros(d, **f64), torch.ones(d, **f64)
+        Xt = train_X_transformed.to(**f64).contiguous()
+        self.U_train = torch.empty(n, d, **f64)
+        _lib.check(L.mcacq_scale_inputs(Xt.data_ptr(), n, d, zeros.data_ptr(), ones.data_ptr(),
+                                        self.lengthscale.data_ptr(), self.U_train.data_ptr(), st), "scale_inputs")
+        # K(X_train, X_train) with the hand-written covariance kernel, + noise on the diagonal
+        Ktt = torch.empty(n, npad, **f64)
+        _lib.check(L.mcacq_cov_cross(kernel_id, self.outputscale, self.U_train.data_ptr(), n, self.U_train.data_ptr(),
+                                     n, d, Ktt.data_ptr(), npad, st), "cov_cross(train, train)")
+        Khat = Ktt[:, :n].contiguous()
+        noise = noise.to(**f64).reshape(-1)
+        Khat.diagonal().add_(noise.expand(n))
+        chol = psd_safe_cholesky(Khat)
+        y = train_Y_standardized.to(**f64).reshape(-1)
+        alpha = torch.cholesky_solve((y - self.mean_const).unsqueeze(-1), chol).squeeze(-1)
+        eye = torch.eye(n, **f64)
+        Linv = torch.linalg.solve_triangular(chol, eye, upper=False)
+        del eye, Khat, Ktt
+        self.alpha = torch.zeros(npad, **f64)
+        self.alpha[:n] = alpha
+        self.R = torch.zeros(npad, npad, **f64)
+        self.R[:n, :n] = Linv.mT
+        self.Rt = torch.zeros(npad, npad, **f64)
+        self.Rt[:n, :n] = Linv
+        del Linv
+        self.train_chol = chol
+        self.desc = _lib.Model(
+            n=n, d=d, np=npad, kernel_id=kernel_id, outputscale=self.outputscale, mean_const=self.mean_const,
+            y_mean=self.y_mean, y_std=self.y_std, x_offset=self.x_offset.data_ptr(), x_coef=self.x_coef.data_ptr(),
+            lengthscale=self.lengthscale.data_ptr(), U_train=self.U_train.data_ptr(), alpha=self.alpha.data_ptr(),
+            R=self.R.data_ptr(), Rt=self.Rt.data_ptr(),
+        )
+
+    # ---------------------------------------------------------------- helpers over the C ABI
+    def workspace(self, b: int, q: int, r: int = 0) -> Tensor:
+        nbytes = _lib.lib().mcacq_workspace_bytes(b, q, self.d, self.np, r)
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def scale(self, X: Tensor) -> Tensor:
+        X = X.to(device=self.device, dtype=torch.float64).contiguous()
+        U = torch.empty_like(X)
+        _lib.check(_lib.lib().mcacq_scale_inputs(X.data_ptr(), X.numel() // self.d, self.d, self.x_offset.data_ptr(),
+                                                 self.x_coef.data_ptr(), self.lengthscale.data_ptr(), U.data_ptr(),
+                                                 _lib.stream_ptr()), "scale_inputs")
+        return U
+
+    def contracted_rows(self, U: Tensor) -> Tensor:
+        """A = K(U, U_train) R for a (rows x d) block of scaled inputs -> rows x np."""
+        L = _lib.lib()
+        rows = U.shape[0]
+        f64 = dict(device=self.device, dtype=torch.float64)
+        Kt = torch.empty(rows, self.np, **f64)
+        A = torch.empty(rows, self.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=self.device)
+        st = _lib.stream_ptr()
+        _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), rows, self.U_train.data_ptr(),
+                                     self.n, self.d, Kt.data_ptr(), self.np, st), "cov_cross")
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, rows, self.np, Kt.data_ptr(), self.R.data_ptr(), A.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        return A
+
+    def posterior_blocks(self, X: Tensor) -> tuple[Tensor, Tensor]:
+        """X: b x q x d -> (mean b x q, covar b x q x q) on the original outcome scale."""
+        b, q, d = X.shape
+        X = X.to(device=self.device, dtype=torch.float64).contiguous()
+        f64 = dict(device=self.device, dtype=torch.float64)
+        mean = torch.empty(b, q, **f64)
+        covar = torch.empty(b, q, q, **f64)
+        ws = self.workspace(b, q, 0)
+        _lib.check(_lib.lib().mcacq_posterior(C.byref(self.desc), X.data_ptr(), b, q, mean.data_ptr(), covar.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mcacq_posterior")
+        return mean, covar

@@ -1,0 +1,141 @@
+/*
+ * mcacq_b200.h -- C ABI of the B200-native batched Monte-Carlo acquisition engine.
+ *
+ * Drop-in boundary: these entry points are what a BoTorch-side FFI for the
+ * hot path `AcquisitionFunction.forward(X: b x q x d) -> b` and its gradient would bind.  The
+ * reference's only native precedent is the pybind11 pair `forward` / `backward` of
+ * botorch/csrc/logei_fused.cpp:376-379 wrapped by `_FusedLogAreas(autograd.Function)`
+ * (botorch/acquisition/multi_objective/logei.py:107-169); the functions below play the same role
+ * for qLogEI / qLogNEI on an exact SingleTaskGP:
+ *
+ *   mcacq_acq_forward      replaces  SampleReducingMCAcquisitionFunction.forward
+ *                                    (botorch/acquisition/monte_carlo.py:268-305) with
+ *                                    qLogNEI._get_samples_and_objectives (acquisition/logei.py:527-565),
+ *                                    sample_cached_cholesky (utils/low_rank.py:84-172),
+ *                                    _log_improvement (acquisition/logei.py:688-715),
+ *                                    fatmax / logmeanexp (utils/safe_math.py:328-355, 213-225)
+ *   mcacq_acq_backward     replaces  torch.autograd.grad(losses.sum(), X) (generation/gen.py:466-469)
+ *   mcacq_posterior        replaces  BatchedMultiOutputGPyTorchModel.posterior (models/gpytorch.py:544-610)
+ *                                    + Standardize.untransform_posterior (transforms/outcome.py:431-511)
+ *   mcacq_scale_inputs     replaces  Normalize._transform (transforms/input.py:541-554) + x / lengthscale
+ *   mcacq_cov_cross        replaces  gpytorch RBFKernel/MaternKernel(nu=2.5)/ScaleKernel forward
+ *   mcacq_dgemm_tri        replaces  test_train_covar @ covar_cache (gpytorch exact_predictive_covar)
+ *
+ * Conventions: plain C, no exceptions, no ownership transfer.  Every pointer is a DEVICE pointer to
+ * contiguous row-major fp64 unless it says "host".  The caller (torch) allocates all inputs, outputs
+ * and the workspace; the library never allocates or frees device memory.  `stream` is a cudaStream_t
+ * passed as void*.  Return value: 0 on success, a positive cudaError_t code on CUDA failure, or a
+ * negative MCACQ_E* code on bad arguments.  All kernels are sm_100a only.
+ */
+#ifndef MCACQ_B200_H
+#define MCACQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCACQ_KERNEL_RBF 0       /* o * exp(-0.5 * rho^2)                                  */
+#define MCACQ_KERNEL_MATERN52 1  /* o * (1 + sqrt5 rho + 5/3 rho^2) exp(-sqrt5 rho)         */
+
+#define MCACQ_TRI_UPPER 0 /* B[k][j] != 0 only for k <= j  (forward:  A = Kt * R)          */
+#define MCACQ_TRI_LOWER 1 /* B[k][j] != 0 only for k >= j  (backward: dKt = dA * R^T)      */
+#define MCACQ_TRI_DENSE 2
+
+#define MCACQ_EINVAL (-1)  /* bad argument (null pointer, bad size, misaligned pitch)      */
+#define MCACQ_ELIMIT (-2)  /* q, r, d or S outside the compiled limits                     */
+#define MCACQ_EWORKSPACE (-3) /* workspace too small                                       */
+
+#define MCACQ_MAX_Q 32
+#define MCACQ_MAX_D 64
+
+/* info[b] bits written by mcacq_acq_forward (psd_safe_cholesky semantics, max_tries = 6):   */
+#define MCACQ_INFO_JITTER_MASK 0x7 /* number of jitter escalations applied (0 = none, 1 -> 1e-8, ... 6 -> 1e-3) */
+#define MCACQ_INFO_NOT_PSD 0x8     /* still not PD after 6 tries  (reference: NotPSDError)   */
+#define MCACQ_INFO_NONFINITE 0x10  /* NaN/Inf in the samples      (reference: NanError)      */
+
+/* Fitted-model operands (gpytorch DefaultPredictionStrategy caches + BoTorch transforms).   */
+typedef struct {
+  int32_t n;         /* train points                                                        */
+  int32_t d;         /* input dim (<= MCACQ_MAX_D)                                          */
+  int32_t np;        /* row pitch (in doubles) of every n-wide buffer; multiple of 16, >= n */
+  int32_t kernel_id; /* MCACQ_KERNEL_*                                                      */
+  double outputscale; /* ScaleKernel outputscale (1.0 if absent)                            */
+  double mean_const;  /* ConstantMean constant                                              */
+  double y_mean;      /* Standardize means (0 if no outcome transform)                      */
+  double y_std;       /* Standardize stdvs (1 if no outcome transform)                      */
+  const double* x_offset;    /* [d] Normalize offset      (zeros if no input transform)     */
+  const double* x_coef;      /* [d] Normalize coefficient (ones  if no input transform)     */
+  const double* lengthscale; /* [d] ARD lengthscales                                        */
+  const double* U_train;     /* [n x d] ((X_train - offset) / coef) / lengthscale           */
+  const double* alpha;       /* [np] mean_cache = (K + noise)^{-1} (y - c), zero padded     */
+  const double* R;           /* [np x np] covar_cache = L^{-T}, upper triangular, zero padded */
+  const double* Rt;          /* [np x np] transpose of R (lower triangular), zero padded    */
+} mcacq_model;
+
+/* qLogNEI baseline operands (acquisition/logei.py:393-459); r == 0 for qLogEI.             */
+typedef struct {
+  int32_t r;             /* number of baseline points                                       */
+  int32_t _pad;
+  const double* U_base;  /* [r x d] scaled baseline inputs                                  */
+  const double* A_base;  /* [r x np] K(X_base, X_train) R                                   */
+  const double* L_base;  /* [r x r] lower Cholesky of the (untransformed) posterior cov of f(X_base) */
+} mcacq_baseline;
+
+/* Monte-Carlo operands.                                                                     */
+typedef struct {
+  int32_t S;           /* number of MC samples                                              */
+  int32_t fat;         /* 1: log_fatplus + fatmax, 0: log_softplus + smooth_amax            */
+  double tau_relu;
+  double tau_max;
+  const double* Zt;    /* [(r + q) x S] base samples, TRANSPOSED (sample index contiguous)  */
+  const double* best;  /* [S] per-sample incumbent (qLogEI: best_f repeated)                */
+} mcacq_mc;
+
+const char* mcacq_version(void);
+int mcacq_num_sms(void);
+
+/* u = ((x - offset) / coef) / lengthscale for `rows` points.                                */
+int mcacq_scale_inputs(const double* X, int64_t rows, int d, const double* x_offset, const double* x_coef,
+                       const double* lengthscale, double* U, void* stream);
+
+/* K[i][j] = k(U1[i], U2[j]) for i < m1, j < m2; columns m2..ldk-1 of each row are zero-filled. */
+int mcacq_cov_cross(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
+                    int d, double* K, int64_t ldk, void* stream);
+
+/* dU1[i][:] = sum_j W[i][j] * d k(U1[i], U2[j]) / d U1[i]   (+= if accumulate).             */
+int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
+                        int d, const double* W, int64_t ldw, const double* row_scale, const double* col_vec,
+                        double* dU1, int accumulate, void* stream);
+
+/* C[M x N] = A[M x K] * B[K x N], N == K == np (multiple of 16), fp64 DMMA, triangular-aware.
+ * `tile_counter` is a 4-byte device scratch word (zeroed by the call).                      */
+int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A, const double* B, double* C,
+                    int32_t* tile_counter, void* stream);
+
+size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
+
+/* Posterior over b q-batches: mean [b x q], covar [b x q x q] on the original outcome scale. */
+int mcacq_posterior(const mcacq_model* model, const double* X, int64_t b, int q, double* mean, double* covar,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* acq[b] = logmeanexp_S( fatmax_q( log_fatplus( y - best ) ) );  info[b] = Cholesky status.
+ * The workspace must be kept intact between a forward and its backward.                      */
+int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc, const double* X,
+                      int64_t b, int q, double* acq, int32_t* info, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* grad_X[b x q x d] = d( sum_b grad_acq[b] * acq[b] ) / dX.                                  */
+int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc, const double* X,
+                       int64_t b, int q, const double* acq, const double* grad_acq, double* grad_X,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last forward/backward call on this thread launched (for bench accounting). */
+int mcacq_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCACQ_B200_H */
