@@ -63,7 +63,7 @@ _lib = None
 
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
-    "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_acq_forward", "mcacq_acq_backward",
+    "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
     "mcacq_last_launch_count",
 ]
 
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.mcacq_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     L.mcacq_workspace_bytes.restype = sz
     L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]
+    L.mcacq_posterior_backward.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, vp, sz, vp]
     L.mcacq_acq_forward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, sz, vp]
     L.mcacq_acq_backward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, vp, sz, vp]
     for name in EXPORTS:

@@ -1,0 +1,5 @@
+from .acquisition import AcquisitionFunction, MCSamplerMixin  # noqa: F401
+from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement  # noqa: F401
+from .monte_carlo import MCAcquisitionFunction, SampleReducingMCAcquisitionFunction  # noqa: F401
+from .objective import (GenericMCObjective, IdentityMCObjective, LinearMCObjective, MCAcquisitionObjective,  # noqa: F401
+                        PosteriorTransform)

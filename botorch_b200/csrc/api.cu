@@ -131,6 +131,44 @@ extern "C" int mcacq_posterior(const mcacq_model* model, const double* X, int64_
   return run_posterior_stage(model, nullptr, X, b, q, w, (cudaStream_t)stream);
 }
 
+// shared tail of the backward pass: blocks_bwd -> dgemm (lower) -> cov bwd -> unscale
+static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline* base, int64_t b, int q,
+                                  const double* gmean, const double* gSxx, const double* gSxb, Workspace& w,
+                                  double* grad_X, cudaStream_t st) {
+  const int r = base ? base->r : 0;
+  const int64_t M = b * q;
+  int rc;
+  BlocksBwdParams bp;
+  bp.b = b; bp.q = q; bp.d = model->d; bp.np = model->np; bp.r = r;
+  bp.kernel_id = model->kernel_id; bp.outputscale = model->outputscale; bp.y_std = model->y_std;
+  bp.A = w.A;
+  bp.A_base = r > 0 ? base->A_base : nullptr;
+  bp.U = w.U;
+  bp.U_base = r > 0 ? base->U_base : nullptr;
+  bp.gmean = gmean; bp.gSxx = gSxx; bp.gSxb = gSxb;
+  bp.row_scale = w.row_scale; bp.dU = w.dU;
+  if ((rc = posterior_blocks_bwd(bp, st))) return rc;
+  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
+  if ((rc = mcacq_cov_cross_bwd(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
+                                model->np, w.row_scale, model->alpha, w.dU, /*accumulate=*/1, st)))
+    return rc;
+  return unscale_grad(w.dU, M, model->d, model->x_coef, model->lengthscale, grad_X, st);
+}
+
+extern "C" int mcacq_posterior_backward(const mcacq_model* model, const double* X, int64_t b, int q,
+                                        const double* gmean, const double* gcovar, double* grad_X, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  int rc = check_model(model);
+  if (rc) return rc;
+  if (!X || !gmean || !gcovar || !grad_X || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
+  if (b == 0) return 0;
+  g_launch_count = 0;
+  Workspace w = carve(workspace, b, q, model->d, model->np, 0);
+  if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
+  return run_posterior_backward(model, nullptr, b, q, gmean, gcovar, nullptr, w, grad_X, (cudaStream_t)stream);
+}
+
 static int check_mc(const mcacq_mc* mc) {
   if (!mc || !mc->Zt || !mc->best || mc->S <= 0) return MCACQ_EINVAL;
   if (!(mc->tau_relu > 0.0) || !(mc->tau_max > 0.0)) return MCACQ_EINVAL;
@@ -160,7 +198,7 @@ extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline*
   const int r = base ? base->r : 0;
   if (r < 0) return MCACQ_EINVAL;
   if (r > 0 && (!base->U_base || !base->A_base || !base->L_base)) return MCACQ_EINVAL;
-  if (r > 64) return MCACQ_ELIMIT;
+  if (r > MCACQ_MAX_R) return MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
   Workspace w = carve(workspace, b, q, model->d, model->np, r);
@@ -182,34 +220,17 @@ extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline
   if (!X || !acq || !grad_acq || !grad_X || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   const int r = base ? base->r : 0;
-  if (r < 0 || r > 64) return r < 0 ? MCACQ_EINVAL : MCACQ_ELIMIT;
+  if (r < 0 || r > MCACQ_MAX_R) return r < 0 ? MCACQ_EINVAL : MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
   Workspace w = carve(workspace, b, q, model->d, model->np, r);
   if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t M = b * q;
-
   SRParams sp;
   fill_sr(sp, base, mc, b, q, w);
   sp.acq = const_cast<double*>(acq);
   sp.grad_acq = grad_acq;
   if ((rc = sample_reduce_bwd(sp, st))) return rc;
 
-  BlocksBwdParams bp;
-  bp.b = b; bp.q = q; bp.d = model->d; bp.np = model->np; bp.r = r;
-  bp.kernel_id = model->kernel_id; bp.outputscale = model->outputscale; bp.y_std = model->y_std;
-  bp.A = w.A;
-  bp.A_base = r > 0 ? base->A_base : nullptr;
-  bp.U = w.U;
-  bp.U_base = r > 0 ? base->U_base : nullptr;
-  bp.gmean = w.gmean; bp.gSxx = w.gSxx; bp.gSxb = w.gSxb;
-  bp.row_scale = w.row_scale; bp.dU = w.dU;
-  if ((rc = posterior_blocks_bwd(bp, st))) return rc;
-
-  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
-  if ((rc = mcacq_cov_cross_bwd(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
-                                model->np, w.row_scale, model->alpha, w.dU, /*accumulate=*/1, st)))
-    return rc;
-  return unscale_grad(w.dU, M, model->d, model->x_coef, model->lengthscale, grad_X, st);
+  return run_posterior_backward(model, base, b, q, w.gmean, w.gSxx, w.gSxb, w, grad_X, st);
 }

@@ -203,10 +203,6 @@ extern "C" int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A,
   }
   int64_t m_tiles = (M + BM - 1) / BM;
   int n_tiles = (np + BN - 1) / BN;
-  // tile slots: full groups of GROUP_M rows; the short last group keeps GROUP_M*n_tiles slots (extra ones skipped)
-  int64_t groups = (m_tiles + GROUP_M - 1) / GROUP_M;
-  int64_t slots = groups * GROUP_M * n_tiles;
-  (void)slots;
   int grid = (int)((m_tiles * n_tiles < sms) ? m_tiles * n_tiles : sms);
   zero_counter_kernel<<<1, 1, 0, st>>>(tile_counter);
   dgemm_tri_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tri_mode, M, np, A, B, C, tile_counter);

@@ -149,3 +149,29 @@ class DevicePredictionStrategy:
         _lib.check(_lib.lib().mcacq_posterior(C.byref(self.desc), X.data_ptr(), b, q, mean.data_ptr(), covar.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mcacq_posterior")
         return mean, covar
+
+    def joint_posterior(self, X: Tensor) -> tuple[Tensor, Tensor]:
+        """Joint posterior over N points (N may exceed the fused kernels' q limit): mean [N], covar [N x N].
+
+        Setup-time route (qLogNEI baseline, prune_inferior_points, Thompson-style candidate sets): the
+        cross-covariance and the contraction `A = K(X, X_train) R` run in the hand-written kernels; the
+        N x N Gram `A A^T` is one library matmul."""
+        X = X.to(device=self.device, dtype=torch.float64).reshape(-1, self.d).contiguous()
+        N = X.shape[0]
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        U = self.scale(X)
+        f64 = dict(device=self.device, dtype=torch.float64)
+        Kt = torch.empty(N, self.np, **f64)
+        _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, self.U_train.data_ptr(),
+                                     self.n, self.d, Kt.data_ptr(), self.np, st), "cov_cross")
+        A = torch.empty(N, self.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=self.device)
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, N, self.np, Kt.data_ptr(), self.R.data_ptr(), A.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        Kxx = torch.empty(N, N, **f64)
+        _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, U.data_ptr(), N, self.d,
+                                     Kxx.data_ptr(), N, st), "cov_cross")
+        mean = self.y_mean + self.y_std * (self.mean_const + Kt @ self.alpha)
+        covar = (self.y_std**2) * (Kxx - A @ A.mT)
+        return mean, covar

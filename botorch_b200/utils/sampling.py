@@ -1,0 +1,68 @@
+"""Host-side quasi-random draws with the reference's seed semantics (botorch/utils/sampling.py).
+
+These stay on the host exactly as in the reference (`gen_batch_initial_conditions` keeps `X_rnd` on
+CPU, optim/initializers.py:384): `torch.quasirandom.SobolEngine` is torch's own generator, so a given
+seed yields bit-identical points, which is what makes selected restart indices comparable.
+"""
+from __future__ import annotations
+
+import math
+from contextlib import contextmanager
+
+import torch
+from torch import Tensor
+from torch.quasirandom import SobolEngine
+
+
+@contextmanager
+def manual_seed(seed: int | None = None):
+    """Temporarily seed torch's global CPU generator (reference :51-71)."""
+    old_state = torch.random.get_rng_state()
+    try:
+        if seed is not None:
+            torch.random.manual_seed(seed)
+        yield
+    finally:
+        if seed is not None:
+            torch.random.set_rng_state(old_state)
+
+
+def draw_sobol_samples(bounds: Tensor, n: int, q: int, batch_shape=None, seed: int | None = None) -> Tensor:
+    """`n x batch_shape x q x d` scrambled-Sobol points inside `bounds` (reference :74-111)."""
+    batch_shape = torch.Size(batch_shape or ())
+    nb = batch_shape.numel()
+    d = bounds.shape[-1]
+    raw = SobolEngine(q * d, scramble=True, seed=seed).draw(nb * n, dtype=bounds.dtype)
+    raw = raw.view(*batch_shape, n, q, d).to(device=bounds.device)
+    if len(batch_shape) > 0:
+        raw = raw.permute(-3, *range(len(batch_shape)), -2, -1)
+    return raw * (bounds[1] - bounds[0]) + bounds[0]
+
+
+def draw_sobol_normal_samples(d: int, n: int, device=None, dtype=None, seed: int | None = None) -> Tensor:
+    """`n x d` qMC N(0, I) draws by inverse-CDF of scrambled Sobol points (reference :114-143 and
+    sampling/qmc.py:77-83: v = 0.5 + (1 - eps)(u - 0.5); z = sqrt(2) erfinv(2v - 1))."""
+    dtype = torch.get_default_dtype() if dtype is None else dtype
+    u = SobolEngine(dimension=d, scramble=True, seed=seed).draw(n, dtype=dtype)
+    v = 0.5 + (1 - torch.finfo(u.dtype).eps) * (u - 0.5)
+    return (torch.erfinv(2 * v - 1) * math.sqrt(2)).to(device=device)
+
+
+def batched_multinomial(weights: Tensor, num_samples: int, replacement: bool = False, generator=None) -> Tensor:
+    """`torch.multinomial` over the last dim for arbitrarily batched weights (reference :317-351)."""
+    flat = weights.reshape(-1, weights.shape[-1])
+    out = torch.multinomial(flat, num_samples=num_samples, replacement=replacement, generator=generator)
+    return out.view(*weights.shape[:-1], num_samples)
+
+
+def boltzmann_sample(function_values: Tensor, num_samples: int, eta: float, replacement: bool = False,
+                     temp_decrease: float = 0.5) -> Tensor:
+    """Indices drawn with probability proportional to exp(eta * zscore(f)) (reference :1084-1115)."""
+    from .transforms import standardize
+
+    norm_weights = standardize(function_values)
+    weights = torch.exp(eta * norm_weights)
+    while torch.isinf(weights).any():
+        eta *= temp_decrease
+        weights = torch.exp(eta * norm_weights)
+    return batched_multinomial(weights=weights, num_samples=num_samples, replacement=replacement)

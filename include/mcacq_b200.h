@@ -50,6 +50,7 @@ extern "C" {
 
 #define MCACQ_MAX_Q 32
 #define MCACQ_MAX_D 64
+#define MCACQ_MAX_R 64
 
 /* info[b] bits written by mcacq_acq_forward (psd_safe_cholesky semantics, max_tries = 6):   */
 #define MCACQ_INFO_JITTER_MASK 0x7 /* number of jitter escalations applied (0 = none, 1 -> 1e-8, ... 6 -> 1e-3) */
@@ -120,6 +121,12 @@ size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
 /* Posterior over b q-batches: mean [b x q], covar [b x q x q] on the original outcome scale. */
 int mcacq_posterior(const mcacq_model* model, const double* X, int64_t b, int q, double* mean, double* covar,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* grad_X[b x q x d] = d( sum gmean * mean + sum gcovar * covar ) / dX, using the workspace left by the
+ * matching mcacq_posterior call (consumed in place).  Replaces autograd through Model.posterior.      */
+int mcacq_posterior_backward(const mcacq_model* model, const double* X, int64_t b, int q, const double* gmean,
+                             const double* gcovar, double* grad_X, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* acq[b] = logmeanexp_S( fatmax_q( log_fatplus( y - best ) ) );  info[b] = Cholesky status.
  * The workspace must be kept intact between a forward and its backward.                      */
