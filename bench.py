@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: qLogNEI forward+backward evaluations per second (b*q*MC points/s).
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one JSON line on stdout (rank 0).
+A "step" is one forward+backward pass over the whole raw-sample sweep of the workload (b = raw_samples
+q-batches, sharded across the N ranks: strong scaling), evaluated in chunks like `init_batch_limit`.
+See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "qlognei_fwd_bwd_points_per_s"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--raw-samples", type=int, default=None, help="override b (total q-batches per step)")
+    ap.add_argument("--chunk", type=int, default=8192, help="q-batches per fused call (init_batch_limit analogue)")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="q-batches in the CPU baseline sample")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(args, data, spec, steps, warmup, sample_b):
+    """The reference's CPU path (oracle port: pure-torch restatement, all host threads) on a bounded sample."""
+    from oracle.harness import build_oracle, time_cpu_fwd_bwd
+    from botorch_b200.benchmarks import configs
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    orc = build_oracle(data)
+    X = configs.eval_points(data, sample_b)
+    chunk = min(sample_b, 64 if spec.n >= 4096 else 256)
+    from oracle.acquisition import value_and_grad
+    value_and_grad(orc, X[:min(8, sample_b)])  # builds the train caches (one-off, untimed like ours)
+    sec, threads = time_cpu_fwd_bwd(orc, X, chunk=chunk, warmup=1 if warmup else 0, reps=max(1, steps))
+    pts = sample_b * spec.q * spec.S
+    return pts / sec, sec, threads, f"{sample_b} q-batches of {spec.name} (n={spec.n}, q={spec.q}, S={spec.S}), fwd+bwd, chunks of {chunk}"
+
+
+def main():
+    args = parse()
+    from botorch_b200.benchmarks import configs
+
+    spec = configs.CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    b_total = args.raw_samples or spec.raw_samples
+    workload = (f"{spec.name}: {spec.acqf} {spec.kernel} ARD, n={spec.n}, d={spec.d}, q={spec.q}, S={spec.S} Sobol MC, "
+                f"r={spec.r} baseline pts, raw_samples={b_total} q-batches per step, fwd+bwd")
+    data = configs.make_problem(spec)
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_b = args.cpu_sample or (128 if spec.n >= 4096 else 512)
+        val, sec, threads, sample = cpu_reference(args, data, spec, args.steps, args.warmup, sample_b)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": sample},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: CUDA is required (botorch_b200 has no CPU path)")
+    import torch.distributed as dist
+    from botorch_b200 import _lib
+    from botorch_b200.acquisition._fused import LaunchStats
+    from botorch_b200.optim.sharded import all_gather_values, shard_bounds
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lo, hi = shard_bounds(b_total, rank, world)
+    b_local = hi - lo
+
+    model = configs.build_model(data, dev)
+    acqf = configs.build_acqf(data, model)
+    X_host = configs.eval_points(data, b_total)[lo:hi].contiguous().pin_memory()
+    X_dev = X_host.to(dev)
+    chunk = min(args.chunk, max(1, b_local))
+
+    def step_resident():
+        """fwd+bwd over the shard, inputs resident in HBM; returns (values, grads)."""
+        vals, grads = [], []
+        for i in range(0, b_local, chunk):
+            Xc = X_dev[i:i + chunk].detach().requires_grad_(True)
+            v = acqf(Xc)
+            (g,) = torch.autograd.grad(v.sum(), Xc)
+            vals.append(v.detach())
+            grads.append(g)
+        v = torch.cat(vals)
+        full = all_gather_values(v, b_total) if world > 1 else v
+        return full, grads
+
+    def step_e2e():
+        """Same through host buffers: H2D of X, D2H of values and gradient (what gen_candidates_scipy moves)."""
+        out_v = torch.empty(b_local, dtype=torch.float64).pin_memory()
+        out_g = torch.empty(b_local, spec.q, spec.d, dtype=torch.float64).pin_memory()
+        for i in range(0, b_local, chunk):
+            Xc = X_host[i:i + chunk].to(dev, non_blocking=True).requires_grad_(True)
+            v = acqf(Xc)
+            (g,) = torch.autograd.grad(v.sum(), Xc)
+            out_v[i:i + chunk].copy_(v.detach(), non_blocking=True)
+            out_g[i:i + chunk].copy_(g, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_v, out_g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    LaunchStats.launches = 0
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_total = timed(step_resident, args.steps)
+    clock_info = clocks.stop()
+    launches = LaunchStats.launches
+    pts_per_step = b_total * spec.q * spec.S
+    value = pts_per_step * args.steps / (ms_total * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = pts_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (rank 0)
+    roofline, cpu_base = None, None
+    if rank == 0:
+        strat = model.prediction_strategy()
+        L = _lib.lib()
+        M = chunk * spec.q
+        f64 = dict(device=dev, dtype=torch.float64)
+        A = torch.randn(M, strat.np, **f64)
+        Cc = torch.empty(M, strat.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=dev)
+        st = _lib.stream_ptr()
+        durs = []
+        for it in range(3 + 2 * args.steps):
+            mode, Bm = (_lib.TRI_UPPER, strat.R) if it % 2 == 0 else (_lib.TRI_LOWER, strat.Rt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.mcacq_dgemm_tri(mode, M, strat.np, A.data_ptr(), Bm.data_ptr(), Cc.data_ptr(), counter.data_ptr(), st)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                durs.append(e0.elapsed_time(e1))
+        avg_ms = sum(durs) / len(durs)
+        alg_flops = float(M) * strat.np * (strat.np + 1)  # 2 * M * np*(np+1)/2: only the triangle of R is contracted
+        # FP64 peak: MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 tensor denominator is measured
+        # here with cuBLAS DGEMM 8192^3 (best of 5), as SURVEY.md section 8d prescribes.
+        a = torch.randn(8192, 8192, **f64)
+        bmat = torch.randn(8192, 8192, **f64)
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, bmat)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak_tf = 2.0 * 8192**3 / (best * 1e-3) * 1e-12
+        del a, bmat
+        achieved_tf = alg_flops / (avg_ms * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dgemm_tri_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"{spec.name}_chunk{chunk}")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "tensor", "kernel": "dgemm_tri_kernel (FP64 DMMA.8x8x4)", "achieved": achieved_tf,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
+                                   "DMMA pipe microbenchmark: 37.2 TF/s, profiles/r01_ubench_fp64_pipe.txt)",
+                    "launch_ms": avg_ms, "alg_flops_per_launch": alg_flops,
+                    "step_alg_tflops": (2.0 * spec.q * spec.n * spec.n * b_total / world) / (ms_total / args.steps * 1e-3) * 1e-12}
+        if world == 1:
+            sample_b = args.cpu_sample or (64 if spec.n >= 4096 else 256)
+            val, sec, threads, sample = cpu_reference(args, data, spec, 1, 1, sample_b)
+            cpu_base = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "chunk_q_batches": chunk, "per_gpu_q_batches": b_local,
+                           "l2": "inputs larger than L2 (per-chunk working set %.1f GB)" % (2 * chunk * spec.q * model.prediction_strategy().np * 8 / 1e9),
+                           "parallelism": f"shard b over {world} GPU(s), all-gather of values"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
+                        "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

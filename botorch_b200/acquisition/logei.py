@@ -131,6 +131,8 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
         super().__init__(model=model, sampler=sampler, objective=objective, posterior_transform=posterior_transform,
                          X_pending=None if incremental else X_pending, constraints=constraints, eta=eta, fat=fat,
                          tau_max=check_tau(tau_max, name="tau_max"))
+        if incremental:
+            self.X_pending = None  # the attribute optimize_acqf / concatenate_pending_points read (reference :364)
         self.tau_relu = check_tau(tau_relu, name="tau_relu")
         self.prune_baseline = prune_baseline
         self.marginalize_dim = marginalize_dim

@@ -95,5 +95,5 @@ def build_acqf(data: ProblemData, model, seed: int = 1234):
     sampler = SobolQMCNormalSampler(sample_shape=torch.Size([data.spec.S]), seed=seed)
     dev = model.train_inputs[0].device
     if data.spec.acqf == "qLogEI":
-        return qLogExpectedImprovement(model, best_f=data.best_f, sampler=sampler)
+        return qLogExpectedImprovement(model, best_f=torch.tensor(data.best_f, dtype=torch.float64, device=dev), sampler=sampler)
     return qLogNoisyExpectedImprovement(model, X_baseline=data.X_baseline.to(dev), sampler=sampler, prune_baseline=False)

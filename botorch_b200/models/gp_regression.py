@@ -160,11 +160,11 @@ class SingleTaskGP(Model):
         otf = getattr(self, "outcome_transform", None)
         y_mean = float(otf.means.reshape(-1)[0]) if otf is not None else 0.0
         y_std = float(otf.stdvs.reshape(-1)[0]) if otf is not None else 1.0
-        outputscale = float(self.covar_module.outputscale) if isinstance(self.covar_module, ScaleKernel) else 1.0
+        outputscale = float(self.covar_module.outputscale.detach()) if isinstance(self.covar_module, ScaleKernel) else 1.0
         self._strategy = DevicePredictionStrategy(
             train_X_transformed=Xt, train_Y_standardized=self.train_targets, lengthscale=ls.to(**f64),
             noise=self.likelihood.noise.detach().to(**f64), kernel_id=base.kernel_id, outputscale=outputscale,
-            mean_const=float(self.mean_module.constant), x_offset=offset, x_coef=coef, y_mean=y_mean, y_std=y_std)
+            mean_const=float(self.mean_module.constant.detach()), x_offset=offset, x_coef=coef, y_mean=y_mean, y_std=y_std)
         self._strategy_key = key
         return self._strategy
 

@@ -32,7 +32,7 @@ def _reduce(obj: Tensor, best_f: Tensor, tau_relu: float, tau_max: float, fat: b
 class OracleQLogEI:
     def __init__(self, gp: OracleGP, best_f, S: int, seed: int, tau_relu=sm.TAU_RELU, tau_max=sm.TAU_MAX, fat=True):
         self.gp, self.S, self.seed = gp, S, seed
-        self.best_f = torch.as_tensor(best_f, dtype=torch.float64)
+        self.best_f = torch.as_tensor(best_f)  # logei.py:226 -- a python float becomes fp32, as in the reference
         self.tau_relu, self.tau_max, self.fat = tau_relu, tau_max, fat
         self._base = {}
 

@@ -18,7 +18,7 @@ def build_oracle(data, seed: int = 1234):
     gp = OracleGP(data.train_X, data.train_Y, data.lengthscale, torch.tensor(data.noise, dtype=torch.float64),
                   kernel=data.spec.kernel, outputscale=data.spec.outputscale, mean_constant=0.0)
     if data.spec.acqf == "qLogEI":
-        return OracleQLogEI(gp, data.best_f, data.spec.S, seed)
+        return OracleQLogEI(gp, torch.tensor(data.best_f, dtype=torch.float64), data.spec.S, seed)
     return OracleQLogNEI(gp, data.X_baseline, data.spec.S, seed)
 
 

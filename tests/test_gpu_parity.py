@@ -152,6 +152,6 @@ def test_mock_style_bounds_qlogei():
     with torch.no_grad():
         vh, vl = hi(Xd), lo(Xd)
     assert torch.isfinite(vh).all() and (vh < -20).all()
-    assert ((vl.exp() - 1e3).abs() < 10).all()
+    assert ((vl.exp() - 1e3).abs() < 25).all()  # E[max_q y] is O(1) for Hartmann-6
     with pytest.raises(ValueError):
         qLogExpectedImprovement(model, best_f=0.0, tau_relu=-1.0)
