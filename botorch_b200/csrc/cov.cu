@@ -100,94 +100,136 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
 }
 
 // ---------------------------------------------------------------------------------------------
-// Backward: dU1[i][:] (+)= sum_j (W[i][j] + row_scale[i] * col_vec[j]) * g(sq_ij) * (u1_i - u2_j).
-// One warp owns RPW rows; lanes stride over the columns of a 128-wide U2 tile staged dimension-major
-// in shared memory; per-dimension partial sums live in registers and are shuffle-reduced at the end.
-constexpr int BW_COLS = 128;
-constexpr int BW_WARPS = 8;
+// Backward: dU1[i][:] (+)= sum_j G[i][j] * (u1_i - u2_j),  G[i][j] = (W[i][j] + row_scale[i] * col_vec[j]) * g(sq_ij)
+// evaluated in the split form  u1_i * (sum_j G[i][j]) - (G U2)[i][:]  (the same form autograd produces for the
+// reference's GEMM-expanded distance).  One CTA owns 64 rows and sweeps the columns in tiles of 64:
+//   phase 1 (SIMT, 4 x 4 outputs per thread as in the forward kernel): sq, g(sq), G tile -> shared memory;
+//   phase 2 (tensor pipe): V[64 x DP] += G[64 x 64] * [U2 | 1][64 x DP] with DMMA.8x8x4, one 8-row tile per warp;
+//   the extra all-ones column yields the row sums for free.
+constexpr int BW_T = 64;        // rows per CTA and columns per tile
+constexpr int BW_P = BW_T + 4;  // padded pitch: conflict-free 8x4 / 4x8 fragment reads
 
-template <int DMAX, bool KEEP_DF>
-__global__ void __launch_bounds__(BW_WARPS * 32)
+__device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int NTD>  // number of 8-wide dimension tiles: 8 * NTD >= d + 1
+__global__ void __launch_bounds__(256, 2)
 cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict__ U1, int64_t m1,
                      const double* __restrict__ U2, int m2, int d, const double* __restrict__ W, int64_t ldw,
                      const double* __restrict__ row_scale, const double* __restrict__ col_vec,
                      double* __restrict__ dU1, int accumulate) {
-  extern __shared__ __align__(16) double sm[];
-  double* s2 = sm;                        // [d][BW_COLS]
-  double* sc = sm + (size_t)d * BW_COLS;  // [BW_COLS] col_vec tile
-  double* su = sc + BW_COLS;              // [BW_WARPS][d] row of U1 per warp (only when !KEEP_DF)
+  constexpr int DP = 8 * NTD;
+  extern __shared__ __align__(32) double sm[];
+  double* s1 = sm;                         // [d][BW_T]      U1^T tile (rows of this CTA)
+  double* s2 = s1 + (size_t)d * BW_T;      // [DP][BW_P]     [U2 | 1 | 0]^T tile
+  double* sG = s2 + (size_t)DP * BW_P;     // [BW_T][BW_P]   G tile; reused for V at the end
+  double* sc = sG + (size_t)BW_T * BW_P;   // [BW_T] col_vec tile
+  double* sr = sc + BW_T;                  // [BW_T] row_scale
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t gr = (int64_t)blockIdx.x * BW_WARPS + warp;
-  const bool row_ok = gr < m1;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * BW_T;
 
-  double u1[KEEP_DF ? DMAX : 1];
-  double acc[DMAX];
-  const double rs = (row_scale != nullptr && row_ok) ? row_scale[gr] : 0.0;
+  for (int idx = tid; idx < BW_T * d; idx += 256) {
+    int p = idx / d, k = idx - p * d;
+    int64_t gr = row0 + p;
+    s1[k * BW_T + p] = (gr < m1) ? U1[gr * d + k] : 0.0;
+  }
+  for (int p = tid; p < BW_T; p += 256) {
+    int64_t gr = row0 + p;
+    sr[p] = (row_scale != nullptr && gr < m1) ? row_scale[gr] : 0.0;
+  }
+  // constant rows of the B operand: row d = ones (row sums), rows d+1.. = zeros
+  for (int idx = tid; idx < (DP - d) * BW_P; idx += 256) s2[(size_t)d * BW_P + idx] = (idx < BW_P) ? 1.0 : 0.0;
+
+  double vacc[NTD][2];
 #pragma unroll
-  for (int k = 0; k < DMAX; k++) {
-    acc[k] = 0.0;
-    if (KEEP_DF) u1[k] = (k < d && row_ok) ? U1[gr * d + k] : 0.0;
-  }
-  if (!KEEP_DF) {
-    for (int k = lane; k < d; k += 32) su[warp * d + k] = row_ok ? U1[gr * d + k] : 0.0;
-  }
+  for (int j = 0; j < NTD; j++) { vacc[j][0] = 0.0; vacc[j][1] = 0.0; }
 
-  for (int c0 = 0; c0 < m2; c0 += BW_COLS) {
-    __syncthreads();
-    for (int idx = tid; idx < BW_COLS * d; idx += BW_WARPS * 32) {
+  for (int c0 = 0; c0 < m2; c0 += BW_T) {
+    __syncthreads();  // previous tile's DMMA reads of s2 / sG are done
+    for (int idx = tid; idx < BW_T * d; idx += 256) {
       int p = idx / d, k = idx - p * d;
       int gc = c0 + p;
-      s2[k * BW_COLS + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
+      s2[k * BW_P + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
     }
-    for (int p = tid; p < BW_COLS; p += BW_WARPS * 32) {
+    for (int p = tid; p < BW_T; p += 256) {
       int gc = c0 + p;
       sc[p] = (col_vec != nullptr && gc < m2) ? col_vec[gc] : 0.0;
     }
     __syncthreads();
-    if (!row_ok) continue;
+    // ---- phase 1
+    double sq[4][4];
 #pragma unroll
-    for (int cc = 0; cc < BW_COLS; cc += 32) {
-      const int p = cc + lane;
-      const int gc = c0 + p;
-      if (gc < m2) {
-        const double w = W[gr * ldw + gc] + rs * sc[p];
-        double sq = 0.0;
-        if (KEEP_DF) {
-          double df[DMAX];
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int k = 0; k < DMAX; k++) {
-            if (k < d) {
-              df[k] = u1[k] - s2[k * BW_COLS + p];
-              sq = fma(df[k], df[k], sq);
-            }
-          }
-          const double wg = w * kernel_dfactor(kernel_id, outputscale, sq);
+      for (int j = 0; j < 4; j++) sq[i][j] = 0.0;
+    for (int k = 0; k < d; k++) {
+      const double4 a4 = *reinterpret_cast<const double4*>(s1 + k * BW_T + ty * 4);
+      const double4 b4 = *reinterpret_cast<const double4*>(s2 + k * BW_P + tx * 4);
+      const double a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const double bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int k = 0; k < DMAX; k++)
-            if (k < d) acc[k] = fma(wg, df[k], acc[k]);
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double df = a[i] - bb[j];
+          sq[i][j] = fma(df, df, sq[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t gr = row0 + ty * 4 + i;
+      const int gc0 = c0 + tx * 4;
+      double w[4] = {0.0, 0.0, 0.0, 0.0};
+      if (gr < m1) {
+        const double* wp = W + gr * ldw + gc0;
+        if (gc0 + 3 < m2 && ((ldw & 1) == 0)) {
+          double2 w01 = *reinterpret_cast<const double2*>(wp);
+          double2 w23 = *reinterpret_cast<const double2*>(wp + 2);
+          w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
         } else {
 #pragma unroll
-          for (int k = 0; k < DMAX; k++) {
-            if (k < d) {
-              double df = su[warp * d + k] - s2[k * BW_COLS + p];
-              sq = fma(df, df, sq);
-            }
-          }
-          const double wg = w * kernel_dfactor(kernel_id, outputscale, sq);
-#pragma unroll
-          for (int k = 0; k < DMAX; k++)
-            if (k < d) acc[k] = fma(wg, su[warp * d + k] - s2[k * BW_COLS + p], acc[k]);
+          for (int j = 0; j < 4; j++) if (gc0 + j < m2) w[j] = wp[j];
         }
       }
+      const double rs = sr[ty * 4 + i];
+      double gv[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool ok = (gr < m1) && (gc0 + j < m2);
+        gv[j] = ok ? (w[j] + rs * sc[tx * 4 + j]) * kernel_dfactor(kernel_id, outputscale, sq[i][j]) : 0.0;
+      }
+      *reinterpret_cast<double4*>(sG + (ty * 4 + i) * BW_P + tx * 4) = make_double4(gv[0], gv[1], gv[2], gv[3]);
+    }
+    __syncthreads();
+    // ---- phase 2: warp `warp` owns rows 8*warp .. 8*warp+7
+    const double* ga = sG + (warp * 8 + g) * BW_P + t4;
+    const double* ub = s2 + (size_t)g * BW_P + t4;
+#pragma unroll 4
+    for (int kk = 0; kk < BW_T; kk += 4) {
+      const double a = ga[kk];
+#pragma unroll
+      for (int j = 0; j < NTD; j++) dmma884c(vacc[j][0], vacc[j][1], a, ub[(size_t)j * 8 * BW_P + kk]);
     }
   }
-
+  __syncthreads();
+  // ---- finalize: V -> shared, dU1[row][k] = u1[row][k] * rowsum[row] - V[row][k]
+  double* sV = sG;  // [BW_T][DP]
 #pragma unroll
-  for (int k = 0; k < DMAX; k++) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && k < d && row_ok) {
+  for (int j = 0; j < NTD; j++) {
+    sV[(warp * 8 + g) * DP + j * 8 + 2 * t4] = vacc[j][0];
+    sV[(warp * 8 + g) * DP + j * 8 + 2 * t4 + 1] = vacc[j][1];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < BW_T * d; idx += 256) {
+    int p = idx / d, k = idx - p * d;
+    int64_t gr = row0 + p;
+    if (gr < m1) {
+      double v = s1[k * BW_T + p] * sV[p * DP + d] - sV[p * DP + k];
       double* dst = dU1 + gr * d + k;
       *dst = accumulate ? (*dst + v) : v;
     }
@@ -254,17 +296,17 @@ extern "C" int mcacq_cov_cross(int kernel_id, double outputscale, const double* 
 }
 
 namespace mcacq {
-template <int DMAX, bool KEEP_DF>
+template <int NTD>
 static int launch_cov_bwd(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
                           int d, const double* W, int64_t ldw, const double* row_scale, const double* col_vec,
                           double* dU1, int accumulate, cudaStream_t st) {
-  size_t smem = ((size_t)d * BW_COLS + BW_COLS + (size_t)BW_WARPS * d) * sizeof(double);
-  auto kern = cov_cross_bwd_kernel<DMAX, KEEP_DF>;
+  constexpr int DP = 8 * NTD;
+  size_t smem = ((size_t)d * BW_T + (size_t)DP * BW_P + (size_t)BW_T * BW_P + 2 * BW_T) * sizeof(double);
+  auto kern = cov_cross_bwd_kernel<NTD>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int64_t rows_per_cta = (int64_t)BW_WARPS;
-  int64_t blocks = (m1 + rows_per_cta - 1) / rows_per_cta;
-  kern<<<(unsigned)blocks, BW_WARPS * 32, smem, st>>>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale,
-                                                      col_vec, dU1, accumulate);
+  int64_t blocks = (m1 + BW_T - 1) / BW_T;
+  kern<<<(unsigned)blocks, 256, smem, st>>>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1,
+                                            accumulate);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
@@ -279,13 +321,14 @@ extern "C" int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const doub
   if (d > MCACQ_MAX_D) return MCACQ_ELIMIT;
   if (m1 == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define MCACQ_BWD_CASE(DM, RP) \
-  return launch_cov_bwd<DM, RP>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate, st)
-  if (d <= 8) MCACQ_BWD_CASE(8, true);
-  if (d <= 16) MCACQ_BWD_CASE(16, true);
-  if (d <= 24) MCACQ_BWD_CASE(24, true);
-  if (d <= 32) MCACQ_BWD_CASE(32, true);
-  if (d <= 48) MCACQ_BWD_CASE(48, false);
-  MCACQ_BWD_CASE(64, false);
+#define MCACQ_BWD_CASE(NT) \
+  return launch_cov_bwd<NT>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate, st)
+  const int ntd = (d + 1 + 7) / 8;  // 8 * NTD >= d + 1 (one extra all-ones column for the row sums)
+  if (ntd <= 1) MCACQ_BWD_CASE(1);
+  if (ntd <= 2) MCACQ_BWD_CASE(2);
+  if (ntd <= 3) MCACQ_BWD_CASE(3);
+  if (ntd <= 4) MCACQ_BWD_CASE(4);
+  if (ntd <= 6) MCACQ_BWD_CASE(6);
+  MCACQ_BWD_CASE(9);
 #undef MCACQ_BWD_CASE
 }
