@@ -1,0 +1,134 @@
+"""CPU tests of the host-side optimisation callers with a mock acquisition function (reference strategy:
+test/optim/test_initializers.py, test/generation/test_gen.py, test/optim/test_batched_lbfgs_b.py)."""
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import minimize
+
+
+class QuadraticAcqf(torch.nn.Module):
+    """acq(X) = -sum_q ||x - c||^2 : maximum at x = c (differentiable, batch independent)."""
+
+    X_pending = None
+
+    def __init__(self, c):
+        super().__init__()
+        self.c = c
+
+    def set_X_pending(self, X):
+        self.X_pending = X
+
+    def forward(self, X):
+        return -((X - self.c) ** 2).sum(dim=(-1, -2))
+
+
+def test_batched_lbfgsb_matches_scipy_per_problem():
+    from botorch_b200.optim.batched_lbfgs_b import fmin_l_bfgs_b_batched
+
+    rng = np.random.default_rng(0)
+    N, D = 7, 5
+    A = rng.normal(size=(N, D, D))
+    Q = np.einsum("nij,nkj->nik", A, A) + 0.5 * np.eye(D)
+    c = rng.normal(size=(N, D))
+    calls = []
+
+    def func(X, batch_indices):
+        calls.append(len(batch_indices))
+        idx = np.array(batch_indices)
+        diff = X - c[idx]
+        f = 0.5 * np.einsum("ni,nij,nj->n", diff, Q[idx], diff) + np.cos(X).sum(-1)
+        g = np.einsum("nij,nj->ni", Q[idx], diff) - np.sin(X)
+        return f, g
+
+    x0 = rng.normal(size=(N, D))
+    bounds = [(-1.0, 1.5)] * D
+    xs, fs, results = fmin_l_bfgs_b_batched(func, x0, bounds=bounds, maxiter=200, pass_batch_indices=True)
+    assert max(calls) == N and min(calls) >= 1  # evaluations are batched, the active set shrinks
+    for i in range(N):
+        def fi(x, i=i):
+            f, g = func(x[None], [i])
+            return float(f[0]), g[0]
+        ref = minimize(fi, x0[i], jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": 200})
+        assert np.array_equal(ref.x, xs[i])  # identical iterates => bit-identical solutions
+        assert ref.fun == fs[i] and ref.nit == results[i].nit
+
+
+def test_batched_lbfgsb_propagates_errors():
+    from botorch_b200.optim.batched_lbfgs_b import fmin_l_bfgs_b_batched
+
+    def bad(X, batch_indices):
+        raise RuntimeError("boom")
+
+    with pytest.raises(RuntimeError, match="boom"):
+        fmin_l_bfgs_b_batched(bad, np.zeros((3, 2)), pass_batch_indices=True)
+
+
+def test_gen_candidates_scipy_reaches_optimum_and_clamps():
+    from botorch_b200.exceptions import BotorchError
+    from botorch_b200.generation import gen_candidates_scipy
+
+    c = torch.tensor([0.3, 0.7, 0.5], dtype=torch.float64)
+    acqf = QuadraticAcqf(c)
+    ics = torch.rand(6, 2, 3, dtype=torch.float64)
+    cand, val = gen_candidates_scipy(ics, acqf, lower_bounds=0.0, upper_bounds=1.0)
+    assert cand.shape == ics.shape and val.shape == (6,)
+    assert torch.allclose(cand, c.expand_as(cand), atol=1e-5)
+    ics_in = ics.clone()
+    ics_in[..., 1] *= 0.6
+    cand2, _ = gen_candidates_scipy(ics_in, acqf, lower_bounds=0.0, upper_bounds=torch.tensor([1.0, 0.6, 1.0]))
+    assert torch.allclose(cand2[..., 1], torch.full_like(cand2[..., 1], 0.6), atol=1e-6)
+    with pytest.raises(BotorchError):
+        gen_candidates_scipy(ics + 2.0, acqf, lower_bounds=0.0, upper_bounds=1.0)
+
+
+def test_nan_gradient_raises_optimization_gradient_error():
+    from botorch_b200.exceptions import OptimizationGradientError
+    from botorch_b200.generation import gen_candidates_scipy
+
+    class NanGrad(QuadraticAcqf):
+        def forward(self, X):
+            return super().forward(X) * torch.tensor(float("nan"), dtype=X.dtype)
+
+    with pytest.raises(OptimizationGradientError):
+        gen_candidates_scipy(torch.rand(2, 1, 3, dtype=torch.float64), NanGrad(torch.zeros(3, dtype=torch.float64)),
+                             lower_bounds=0.0, upper_bounds=1.0)
+
+
+def test_initial_conditions_selection_semantics():
+    from botorch_b200.exceptions import BadInitialCandidatesWarning
+    from botorch_b200.optim import gen_batch_initial_conditions, initialize_q_batch, initialize_q_batch_topn
+
+    bounds = torch.stack([torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)])
+    acqf = QuadraticAcqf(torch.tensor([0.2, 0.2, 0.9], dtype=torch.float64))
+    torch.manual_seed(0)
+    ics = gen_batch_initial_conditions(acqf, bounds, q=2, num_restarts=4, raw_samples=64, options={"seed": 3})
+    assert ics.shape == (4, 2, 3) and (ics >= 0).all() and (ics <= 1).all()
+    torch.manual_seed(0)
+    ics2 = gen_batch_initial_conditions(acqf, bounds, q=2, num_restarts=4, raw_samples=64, options={"seed": 3, "init_batch_limit": 7})
+    assert torch.equal(ics, ics2)  # chunking the sweep does not change the selection
+    X = torch.rand(10, 1, 3, dtype=torch.float64)
+    vals = torch.arange(10, dtype=torch.float64)
+    torch.manual_seed(1)
+    Xs, vs = initialize_q_batch(X, vals, n=3, eta=1.0)
+    assert 9.0 in vs.tolist()  # the arg-max is always included (initializers.py:1028-1030)
+    Xt, vt = initialize_q_batch_topn(X, vals, n=3)
+    assert vt.tolist() == [9.0, 8.0, 7.0]
+    with pytest.warns(BadInitialCandidatesWarning):
+        initialize_q_batch(X, torch.ones(10, dtype=torch.float64), n=3)
+    with pytest.raises(RuntimeError):
+        initialize_q_batch(X, vals, n=11)
+
+
+def test_optimize_acqf_joint_and_sequential():
+    from botorch_b200.optim import optimize_acqf
+
+    bounds = torch.stack([torch.zeros(2, dtype=torch.float64), torch.ones(2, dtype=torch.float64)])
+    c = torch.tensor([0.25, 0.6], dtype=torch.float64)
+    acqf = QuadraticAcqf(c)
+    torch.manual_seed(0)
+    cand, val = optimize_acqf(acqf, bounds, q=2, num_restarts=3, raw_samples=32, options={"seed": 0})
+    assert cand.shape == (2, 2) and torch.allclose(cand, c.expand(2, 2), atol=1e-5) and val.ndim == 0
+    allc, allv = optimize_acqf(acqf, bounds, q=2, num_restarts=3, raw_samples=32, options={"seed": 0}, return_best_only=False)
+    assert allc.shape == (3, 2, 2) and allv.shape == (3,)
+    cs, vs = optimize_acqf(acqf, bounds, q=2, num_restarts=3, raw_samples=32, options={"seed": 0}, sequential=True)
+    assert cs.shape == (2, 2) and vs.shape == (2,) and acqf.X_pending is None
