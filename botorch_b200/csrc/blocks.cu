@@ -179,6 +179,7 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
   }
 
   double* Ab = p.A + bb * q * np;
+#pragma unroll 2
   for (int c0 = 0; c0 < np; c0 += 16) {
     const int cc = c0 + 2 * g;  // this lane's two source columns
     double acc[QT][2][2];

@@ -20,7 +20,7 @@
 namespace mcacq {
 
 
-constexpr int SR_THREADS = 256;
+constexpr int SR_THREADS = 128;
 constexpr int SR_WARPS = SR_THREADS / 32;
 
 // ---- utility pieces -----------------------------------------------------------------------------
@@ -315,7 +315,9 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   double* gco = coefT + (size_t)(r + q) * QP;  // [q][NC]  accumulated d/d[B C mean]
   double* smean = gco + (size_t)q * NC;        // [q]
   double* mats = smean + q;                    // 4 x [q][q] scratch: L, P/X, G, gT
-  double* gy = mats + 4 * q * q;               // [chunk][q]
+  const int GP = q | 1;                        // odd pitch for the weight rows
+  double* gy = mats + 4 * q * q;               // [chunk + 3][GP]  per-sample weights (zero padded to a multiple of 4 rows)
+  double* stage = gy + (size_t)(chunk + 4) * GP;  // [SR_WARPS][QMAX][8] cross-warp staging of DMMA partials
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t bb = blockIdx.x;
 
@@ -336,7 +338,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   const double gout = p.grad_acq[bb];
   const double lse_total = p.acq[bb] + log((double)S);
 
-  const int n_out = q * NC;
+
 
   for (int c0 = 0; c0 < S; c0 += chunk) {
     const int cend = (c0 + chunk < S) ? c0 + chunk : S;
@@ -378,27 +380,70 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           double ws;
           if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
           else ws = gout * exp(fm - lse_total);
-          double* gys = gy + (size_t)(s0 + ns - c0) * q;
+          double* gys = gy + (size_t)(s0 + ns - c0) * GP;
 #pragma unroll
           for (int i = 0; i < QMAX; i++) if (i < q) gys[i] = ws * w[i] * dli[i];
         }
       }
     }
     __syncthreads();
-    // ---- pass B: gco[i][j] += sum_s gy[s][i] * Z[s][j]   (j == r+q: the mean column, Z == 1)
-    for (int o = tid; o < n_out; o += SR_THREADS) {
-      const int j = o / q, i = o - j * q;  // i fastest: lanes of a warp share few j rows
-      double a = 0.0;
-      if (j < r + q) {
-        const double* zr = p.Zt + (size_t)j * S + c0;
-        for (int s = 0; s < cend - c0; s++) a = fma(gy[(size_t)s * q + i], zr[s], a);
-      } else {
-        for (int s = 0; s < cend - c0; s++) a += gy[(size_t)s * q + i];
-      }
-      gco[i * NC + j] += a;  // each (i, j) is owned by exactly one thread
+    // zero the padding rows so that the k-loop can run in steps of 4
+    {
+      const int nloc = cend - c0;
+      const int npad = (nloc + 3) & ~3;
+      for (int idx = tid; idx < (npad - nloc) * GP; idx += SR_THREADS) gy[(size_t)nloc * GP + idx] = 0.0;
     }
     __syncthreads();
+    // ---- pass B (tensor pipe): gco[i][j] += sum_s gy[s][i] * Z[s][j]   (j == r+q: the mean column, Z == 1)
+    //      DMMA.8x8x4 with A = gy^T (m = i, k = sample), B = Z (k = sample, n = j); the 4 warps split the samples,
+    //      partial tiles are combined in a fixed order (deterministic).
+    {
+      const int g = lane >> 2, t4 = lane & 3;
+      const int nloc = cend - c0;
+      const int ksteps = (nloc + 3) >> 2;
+      const int per_warp = (ksteps + SR_WARPS - 1) / SR_WARPS;
+      const int k_begin = warp * per_warp;
+      const int k_end = (k_begin + per_warp < ksteps) ? k_begin + per_warp : ksteps;
+      const int ntj = (NC + 7) >> 3;
+      constexpr int MT = QMAX / 8;
+      for (int nj = 0; nj < ntj; nj++) {
+        const int j = nj * 8 + g;
+        const double* zr = (j < r + q) ? p.Zt + (size_t)j * S + c0 : nullptr;
+        const double bconst = (j == r + q) ? 1.0 : 0.0;
+        double acc[MT][2];
+#pragma unroll
+        for (int mi = 0; mi < MT; mi++) { acc[mi][0] = 0.0; acc[mi][1] = 0.0; }
+        for (int kk = k_begin; kk < k_end; kk++) {
+          const int sl = 4 * kk + t4;
+          const double bv = (zr != nullptr) ? ((sl < nloc) ? zr[sl] : 0.0) : bconst;
+#pragma unroll
+          for (int mi = 0; mi < MT; mi++) {
+            const int i = mi * 8 + g;
+            const double av = (i < q) ? gy[(size_t)sl * GP + i] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(acc[mi][0]), "+d"(acc[mi][1]) : "d"(av), "d"(bv));
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; mi++) {
+          stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4] = acc[mi][0];
+          stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4 + 1] = acc[mi][1];
+        }
+        __syncthreads();
+        for (int o = tid; o < QMAX * 8; o += SR_THREADS) {
+          const int i = o >> 3, jj = nj * 8 + (o & 7);
+          if (i < q && jj < NC) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < SR_WARPS; w++) a += stage[(w * QMAX + i) * 8 + (o & 7)];
+            gco[i * NC + jj] += a;
+          }
+        }
+        __syncthreads();
+      }
+    }
   }
+  __syncthreads();
 
   // ---- Cholesky reverse-mode (warp 0): gT = sym( L^{-T} Phi(L^T gL) L^{-1} )
   double* Lm = mats;
@@ -453,7 +498,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
     const int i = idx / r, j = idx - i * r;
     double v = gco[i * NC + j];
     for (int k = 0; k < q; k++) v -= 2.0 * gT[i * q + k] * coefT[j * QP + k];
-    gy[idx] = v;  // reuse gy scratch as gB_tot [q][r]  (chunk*q >= q*r guaranteed by the host)
+    gy[idx] = v;  // reuse gy scratch as gB_tot [q][r]  (chunk*GP >= q*r guaranteed by the host)
   }
   __syncthreads();
   // ---- gSxb = gB_tot L_base^{-1}: backward substitution, one warp per row
@@ -478,9 +523,11 @@ static size_t fwd_smem(int q, int r) {
   return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS) * sizeof(double);
 }
 
-static size_t bwd_smem(int q, int r, int chunk) {
+static size_t bwd_smem(int q, int r, int chunk, int qmax) {
   int QP = (q + 1) & ~1;
-  return ((size_t)(r + q) * QP + (size_t)q * (r + q + 1) + q + 4 * (size_t)q * q + (size_t)chunk * q) * sizeof(double);
+  int GP = q | 1;
+  return ((size_t)(r + q) * QP + (size_t)q * (r + q + 1) + q + 4 * (size_t)q * q + (size_t)(chunk + 4) * GP +
+          (size_t)SR_WARPS * qmax * 8) * sizeof(double);
 }
 
 template <int QMAX, int NS>
@@ -498,12 +545,12 @@ static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
 template <int QMAX, int NS>
 static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
-  int chunk = (64 * 1024) / (8 * p.q);
+  int chunk = (36 * 1024) / (8 * (p.q | 1));
   if (chunk > p.S) chunk = p.S;
   chunk = (chunk / (SR_THREADS * NS)) * (SR_THREADS * NS);
   if (chunk < SR_THREADS * NS) chunk = SR_THREADS * NS;
-  if (chunk < p.r) chunk = p.r;
-  size_t smem = bwd_smem(p.q, p.r, chunk);
+  if ((int64_t)chunk * (p.q | 1) < (int64_t)p.q * p.r) chunk = (p.q * p.r + (p.q | 1) - 1) / (p.q | 1);
+  size_t smem = bwd_smem(p.q, p.r, chunk, QMAX);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
   auto kern = sample_reduce_bwd_kernel<QMAX, NS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -37,7 +37,7 @@ def run(n, d, q, r, S, b, kernel, outputscale, norm):
     print(f"   posterior mean rel {rel(mean_g, mean_o):.2e}  covar rel {rel(cov_g, cov_o):.2e}  var rel(min elem) {float(((cov_g.cpu().diagonal(dim1=-1,dim2=-2)-cov_o.diagonal(dim1=-1,dim2=-2)).abs()/cov_o.diagonal(dim1=-1,dim2=-2)).max()):.2e}")
     if r == 0:
         best_f = float(Y.max())
-        orc = OracleQLogEI(gp, best_f, S, 1234)
+        orc = OracleQLogEI(gp, torch.tensor(best_f, dtype=torch.float64), S, 1234)
         Z = qlogei_base_samples(S, q, 1234).view(S, q)
         best = torch.full((S,), best_f, dtype=torch.float64)
         base = None
