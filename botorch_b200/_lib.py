@@ -64,7 +64,7 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count",
+    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward",
 ]
 
 
@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     L.mcacq_posterior_backward.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, vp, sz, vp]
     L.mcacq_acq_forward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, sz, vp]
     L.mcacq_acq_backward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, vp, sz, vp]
+    L.mcacq_log_areas_forward.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp]
+    L.mcacq_log_areas_backward.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mcacq_version", "mcacq_workspace_bytes"):
@@ -112,7 +114,7 @@ def check(rc: int, what: str) -> None:
 def require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise McacqError(f"{name} must be a CUDA tensor (got {t.device}); botorch_b200 has no CPU path.")
-    if t.dtype != torch.float64 and t.dtype != torch.int32:
+    if t.dtype not in (torch.float64, torch.float32, torch.int32):
         raise McacqError(f"{name} must be float64 (got {t.dtype}).")
     if not t.is_contiguous():
         raise McacqError(f"{name} must be contiguous.")

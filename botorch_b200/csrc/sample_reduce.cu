@@ -24,11 +24,22 @@ constexpr int SR_THREADS = 128;
 constexpr int SR_WARPS = SR_THREADS / 32;
 
 // ---- utility pieces -----------------------------------------------------------------------------
+// Reciprocal to ~1 ulp without the IEEE division slow path: MUFU seed (>= 20 bits) + two Newton steps.
+// Arguments here are always finite, normal and >= 1e-300 (1 + u^2, 2 + 2v + v^2, tau * f).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // log-improvement value and derivative w.r.t. z (the improvement y - best).
 template <bool GRAD>
-__device__ __forceinline__ double log_improve(double z, double tau, int fat, double& dli) {
+__device__ __forceinline__ double log_improve(double z, double tau, double inv_tau, int fat, double& dli) {
   if (fat) {
-    const double u = z / tau;
+    const double u = z * inv_tau;
     double sp, dsp;
     if (u > 20.0) {  // torch softplus threshold
       sp = u; dsp = 1.0;
@@ -39,11 +50,12 @@ __device__ __forceinline__ double log_improve(double z, double tau, int fat, dou
       sp = log1p(e);
       dsp = e / (e + 1.0);
     }
-    const double den = 1.0 + u * u;
-    const double ca = 1.0 / den;
+    const double den = fma(u, u, 1.0);
+    const double ca = (den < 1e300) ? fast_rcp(den) : 0.0;
     const double f = sp + 0.1 * ca;
-    if (GRAD) dli = (dsp - 0.2 * u * ca * ca) / (tau * f);
-    return log(tau * f);
+    const double tf = tau * f;
+    if (GRAD) dli = (dsp - 0.2 * u * ca * ca) * ((tf > 1e-300 && tf < 1e300) ? fast_rcp(tf) : 1.0 / tf);
+    return log(tf);
   } else {
     const double xt = z / tau;
     if (xt > -35.0) {
@@ -63,7 +75,8 @@ __device__ __forceinline__ double log_improve(double z, double tau, int fat, dou
 
 // q-reduction: fatmax (fat) or smooth_amax; optionally the weights d fm / d li_i.
 template <int QMAX, bool GRAD>
-__device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, double tau, int fat, double (&w)[QMAX]) {
+__device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, double tau, double inv_tau, int fat,
+                                           double (&w)[QMAX]) {
   double M = -CUDART_INF;
 #pragma unroll
   for (int i = 0; i < QMAX; i++) if (i < q) M = fmax(M, li[i]);
@@ -84,11 +97,12 @@ __device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, doub
     double dp[QMAX];
 #pragma unroll
     for (int i = 0; i < QMAX; i++) if (i < q) {
-      const double v = (M - li[i]) / tau;
-      const double den = 2.0 + 2.0 * v + v * v;
-      P += 2.0 / den;
+      const double v = (M - li[i]) * inv_tau;
+      const double den = fma(v, v + 2.0, 2.0);
+      const double rden = (den < 1e300) ? fast_rcp(den) : 0.0;
+      P += 2.0 * rden;
       if (GRAD) {
-        dp[i] = -(4.0 + 4.0 * v) / (den * den);
+        dp[i] = -(4.0 + 4.0 * v) * rden * rden;
         dsum += dp[i];
         cnt += (li[i] == M) ? 1 : 0;
       }
@@ -235,6 +249,7 @@ sample_reduce_fwd_kernel(SRParams p) {
   __syncthreads();
 
   // ---- samples: NS samples per thread, coefficients broadcast from shared memory
+  const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
   double lm = -CUDART_INF, ls = 0.0;
   bool nonfinite = false;
   for (int s0 = tid * NS; s0 < S; s0 += SR_THREADS * NS) {
@@ -271,10 +286,10 @@ sample_reduce_fwd_kernel(SRParams p) {
             const double yi = y[ns][i] + smean[i];
             if (!isfinite(yi)) nonfinite = true;
             double dl;
-            li[i] = log_improve<false>(yi - bst, p.tau_relu, p.fat, dl);
+            li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
           } else li[i] = -CUDART_INF;
         }
-        const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, p.fat, wdummy);
+        const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
         if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
         else lse_push(lm, ls, fm);
       }
@@ -337,6 +352,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
 
   const double gout = p.grad_acq[bb];
   const double lse_total = p.acq[bb] + log((double)S);
+  const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
 
 
 
@@ -373,10 +389,10 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           double li[QMAX], dli[QMAX], w[QMAX];
 #pragma unroll
           for (int i = 0; i < QMAX; i++) {
-            if (i < q) li[i] = log_improve<true>(y[ns][i] + smean[i] - bst, p.tau_relu, p.fat, dli[i]);
+            if (i < q) li[i] = log_improve<true>(y[ns][i] + smean[i] - bst, p.tau_relu, inv_tau_relu, p.fat, dli[i]);
             else { li[i] = -CUDART_INF; dli[i] = 0.0; }
           }
-          const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, p.fat, w);
+          const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, inv_tau_max, p.fat, w);
           double ws;
           if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
           else ws = gout * exp(fm - lse_total);

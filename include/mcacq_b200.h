@@ -139,6 +139,21 @@ int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, con
                        int64_t b, int q, const double* acq, const double* grad_acq, double* grad_X,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- qLogEHVI / qLogNEHVI inclusion-exclusion inner loop ---------------------------
+ * CUDA counterpart of botorch/csrc/logei_fused.cpp: `fused_log_areas_forward` (:184-272) and
+ * `fused_log_areas_backward` (:274-374), i.e. the pybind pair `forward` / `backward` (:376-379).
+ *   obj_subsets [B x n_sub x isz x m], cell_lower / cell_upper [B_cells x nc x m] (batched_cells = 0: B_cells = 1,
+ *   batched_cells = 1: B_cells = B)  ->  out [B x nc x n_sub];  backward: grad_out [B x nc x n_sub] ->
+ *   grad_obj [B x n_sub x isz x m].  dtype: 0 = fp64, 1 = fp32.  isz <= 32, m <= 8 (MAX_I / MAX_M, :33-34).
+ * lcl_workspace: B_cells * nc * m elements of scratch (log cell lengths).                                        */
+int mcacq_log_areas_forward(const void* obj_subsets, const void* cell_lower, const void* cell_upper, int64_t B,
+                            int n_sub, int isz, int m, int batched_cells, int nc, int dtype, double tau_relu,
+                            double tau_max, void* out, void* lcl_workspace, void* stream);
+int mcacq_log_areas_backward(const void* grad_out, const void* obj_subsets, const void* cell_lower,
+                             const void* cell_upper, int64_t B, int n_sub, int isz, int m, int batched_cells, int nc,
+                             int dtype, double tau_relu, double tau_max, void* grad_obj, void* lcl_workspace,
+                             void* stream);
+
 /* Number of kernels the last forward/backward call on this thread launched (for bench accounting). */
 int mcacq_last_launch_count(void);
 

@@ -89,6 +89,24 @@ def main():
         v2, g2 = value_and_grad(nei, Xq)
         out[kern] = {"mean": mean, "cov": cov, "qlogei": v1, "qlogei_grad": g1, "qlognei": v2, "qlognei_grad": g2}
     torch.save(out, os.path.join(HERE, "oracle_path_small.pt"))
+    # ---- REAL reference outputs of the compiled botorch/csrc/logei_fused.cpp (oracle/build_ref.py)
+    from oracle.build_ref import build, load_ref
+
+    build()
+    ref = load_ref()
+    torch.manual_seed(2)
+    cases = {}
+    for name, (B, n_sub, isz, m, nc, batched) in {"ehvi": (6, 5, 3, 2, 7, False), "nehvi": (4, 6, 2, 3, 5, True),
+                                                   "single": (3, 4, 1, 4, 3, False), "wide": (2, 3, 9, 2, 4, True)}.items():
+        obj = torch.randn(B, n_sub, isz, m, dtype=torch.float64)
+        lo = torch.randn(*( (B,) if batched else () ), nc, m, dtype=torch.float64) - 0.5
+        hi = lo + torch.rand_like(lo) * 2 + 0.05
+        hi[..., -1, :] = float("inf")  # unbounded top cell, clamped to 1e10 inside the kernel
+        go = torch.randn(B, nc, n_sub, dtype=torch.float64)
+        fwd = ref.forward(obj, lo, hi, 1e-6, 1e-2)
+        bwd = ref.backward(go, obj, lo, hi, 1e-6, 1e-2)
+        cases[name] = {"obj": obj, "lo": lo, "hi": hi, "go": go, "fwd": fwd, "bwd": bwd}
+    torch.save(cases, os.path.join(HERE, "log_areas_ref.pt"))
     print("wrote", sorted(os.listdir(HERE)))
 
 
