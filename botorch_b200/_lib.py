@@ -64,7 +64,7 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward",
+    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt",
 ]
 
 
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.mcacq_cov_cross.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp]
     L.mcacq_cov_cross_bwd.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp, vp, vp, i32, vp]
     L.mcacq_dgemm_tri.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
+    L.mcacq_dgemm_nt.argtypes = [i32, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp]
     L.mcacq_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     L.mcacq_workspace_bytes.restype = sz
     L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]

@@ -1,1 +1,2 @@
 from .gen import gen_candidates_scipy  # noqa: F401
+from .sampling import MaxPosteriorSampling  # noqa: F401

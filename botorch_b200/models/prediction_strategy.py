@@ -172,6 +172,23 @@ class DevicePredictionStrategy:
         Kxx = torch.empty(N, N, **f64)
         _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, U.data_ptr(), N, self.d,
                                      Kxx.data_ptr(), N, st), "cov_cross")
+        G = torch.empty(N, N, **f64)
+        _lib.check(L.mcacq_dgemm_nt(0, N, N, self.np, A.data_ptr(), self.np, A.data_ptr(), self.np, G.data_ptr(), N,
+                                    counter.data_ptr(), st), "dgemm_nt (syrk)")
         mean = self.y_mean + self.y_std * (self.mean_const + Kt @ self.alpha)
-        covar = (self.y_std**2) * (Kxx - A @ A.mT)
+        covar = (self.y_std**2) * (Kxx - G)
         return mean, covar
+
+    def lower_times_samples(self, chol: Tensor, Z: Tensor) -> Tensor:
+        """Y[N x S] = L[N x N] Z[S x N]^T with the triangular-aware DMMA kernel (MultivariateNormal.rsample's
+        `root @ base_samples`)."""
+        N, S = chol.shape[-1], Z.shape[0]
+        if N % 2:
+            raise _lib.McacqError("lower_times_samples needs an even number of points (16-byte row chunks)")
+        chol = chol.contiguous()
+        Z = Z.contiguous()
+        Y = torch.empty(N, S, device=self.device, dtype=torch.float64)
+        counter = torch.zeros(64, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().mcacq_dgemm_nt(1, N, S, N, chol.data_ptr(), N, Z.data_ptr(), N, Y.data_ptr(), S,
+                                             counter.data_ptr(), _lib.stream_ptr()), "dgemm_nt (trmm)")
+        return Y

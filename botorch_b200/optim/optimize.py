@@ -11,7 +11,6 @@ import torch.distributed as dist
 from torch import Tensor
 
 from ..exceptions.errors import UnsupportedError
-from ..generation.gen import gen_candidates_scipy
 from .initializers import gen_batch_initial_conditions
 from .sharded import shard_bounds
 
@@ -34,6 +33,8 @@ def _gather_cat(t: Tensor, sizes: list[int]) -> Tensor:
 def _optimize_acqf_batch(acq_function, bounds: Tensor, q: int, num_restarts: int, raw_samples: int | None,
                          options: dict, batch_initial_conditions: Tensor | None, return_best_only: bool,
                          shard_across_ranks: bool):
+    from ..generation.gen import gen_candidates_scipy  # local import: generation <-> optim are mutually dependent
+
     sharded = shard_across_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if batch_initial_conditions is None:
         if raw_samples is None:

@@ -116,6 +116,12 @@ int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const double* U1, int
 int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A, const double* B, double* C,
                     int32_t* tile_counter, void* stream);
 
+/* C[M x N] = A[M x K] * Bt[N x K]^T (both K-contiguous; lda, ldb, K even).  a_lower = 1: A is lower triangular
+ * (k <= row), only that range is contracted.  Joint-posterior route (generation/sampling.py:89-155): SYRK
+ * `A A^T` of gpytorch exact_predictive_covar and `L z` of MultivariateNormal.rsample.                          */
+int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
+                   double* C, int64_t ldc, int32_t* tile_counter, void* stream);
+
 size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
 
 /* Posterior over b q-batches: mean [b x q], covar [b x q x q] on the original outcome scale. */
