@@ -86,3 +86,21 @@ def fatmax(x: Tensor, dim, keepdim: bool = False, tau=TAU, alpha: float = ALPHA)
 
 def smooth_amax(X: Tensor, dim=-1, keepdim: bool = False, tau=1.0) -> Tensor:
     return logsumexp(X / tau, dim=dim, keepdim=keepdim) * tau
+
+
+def log1mexp(x: Tensor) -> Tensor:
+    """log(1 - exp(x)) for x < 0 (reference :36-46)."""
+    is_small = -math.log(2) < x
+    return torch.where(is_small, (-x.expm1()).log(), (-x.exp()).log1p())
+
+
+def logplusexp(a: Tensor, b: Tensor) -> Tensor:
+    """log(exp(a) + exp(b)) (reference :100-103)."""
+    return logsumexp(torch.stack(torch.broadcast_tensors(a, b), dim=-1), dim=-1)
+
+
+def logdiffexp(log_a: Tensor, log_b: Tensor) -> Tensor:
+    """log(b - a) given log a < log b (reference :106-120)."""
+    log_a, log_b = torch.broadcast_tensors(log_a, log_b)
+    is_inf = log_b == -torch.inf
+    return log_b + log1mexp(log_a - log_b.masked_fill(is_inf, 0.0))

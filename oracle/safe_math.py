@@ -119,3 +119,21 @@ def log_improvement(Y: Tensor, best_f: Tensor, tau, fat: bool) -> Tensor:
     log_soft_clamp = log_fatplus if fat else log_softplus
     Z = Y - best_f.unsqueeze(-1).to(Y)
     return log_soft_clamp(Z, tau=tau)
+
+
+def log1mexp(x: Tensor) -> Tensor:
+    """safe_math.py:36-46."""
+    is_small = -math.log(2) < x
+    return torch.where(is_small, (-x.expm1()).log(), (-x.exp()).log1p())
+
+
+def logplusexp(a: Tensor, b: Tensor) -> Tensor:
+    """safe_math.py:100-103."""
+    return logsumexp(torch.stack(torch.broadcast_tensors(a, b), dim=-1), dim=-1)
+
+
+def logdiffexp(log_a: Tensor, log_b: Tensor) -> Tensor:
+    """safe_math.py:106-120."""
+    log_a, log_b = torch.broadcast_tensors(log_a, log_b)
+    is_inf = log_b == -torch.inf
+    return log_b + log1mexp(log_a - log_b.masked_fill(is_inf, 0.0))
