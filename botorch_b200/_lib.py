@@ -64,7 +64,8 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt",
+    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
+    "mcacq_ozaki_contract",
 ]
 
 
@@ -88,6 +89,8 @@ def lib() -> C.CDLL:
     L.mcacq_cov_cross_bwd.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp, vp, vp, i32, vp]
     L.mcacq_dgemm_tri.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_dgemm_nt.argtypes = [i32, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp]
+    L.mcacq_slice_rows.argtypes = [vp, i64, i32, i64, i32, i32, i32, i32, vp, vp, vp]
+    L.mcacq_ozaki_contract.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
     L.mcacq_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     L.mcacq_workspace_bytes.restype = sz
     L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]
@@ -115,7 +118,7 @@ def check(rc: int, what: str) -> None:
 def require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise McacqError(f"{name} must be a CUDA tensor (got {t.device}); botorch_b200 has no CPU path.")
-    if t.dtype not in (torch.float64, torch.float32, torch.int32):
+    if t.dtype not in (torch.float64, torch.float32, torch.int32, torch.int8):
         raise McacqError(f"{name} must be float64 (got {t.dtype}).")
     if not t.is_contiguous():
         raise McacqError(f"{name} must be contiguous.")

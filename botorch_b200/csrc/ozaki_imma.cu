@@ -1,0 +1,345 @@
+// FP64-accurate contraction on the INT8 tensor cores (tcgen05 `kind::i8`, TMEM int32 accumulators, TMA operands).
+//
+//   C[M x N] (fp64) = A[M x K] * B^T,   B given as rows [N x K] (K contiguous),   triangular-aware in K
+//
+// Ozaki-style error-free splitting: both operands are pre-split into 7-bit signed slices with a power-of-two row
+// scale,  A[i][k] = 2^ea[i] * sum_p A_p[i][k] 128^-(p+1),  B[j][k] = 2^fb[j] * sum_q B_q[j][k] 128^-(q+1)
+// (`slice_rows_kernel` below).  Every slice product A_p B_q^T is EXACT in int32 (K * 127^2 < 2^31), so
+//   C[i][j] = 2^(ea[i] + fb[j]) * sum_{g < G} 128^-(g+2) * S_g[i][j],     S_g = sum_{p+q=g} A_p B_q^T,
+// with truncation error 2^-7G relative to (row max) x (column max): G = 7 diagonals give ~1e-11 on the posterior
+// variance, G = 6 ~1e-9 (measured, tools/ozaki_proto.py).  This is the same contraction as dgemm_tri.cu
+// (gpytorch's `test_train_covar @ covar_cache`), executed at INT8 tensor-core rate instead of the FP64 DMMA pipe.
+//
+// Kernel structure (one persistent CTA per SM, 6 warps):
+//   warp 0 / lane 0 : TMA producer.  Per 64-byte k-block it loads G A-tiles (128 rows x 64 B) and G B-tiles
+//                     (64 rows x 64 B), SWIZZLE_64B, into a 2-stage ring (84 KB per stage at G = 7).
+//   warp 1 / lane 0 : MMA issuer.  All G diagonals S_g live in TMEM at once (G x 64 columns of int32, 448 of 512),
+//                     so one k-block of operands feeds G(G+1)/2 slice products: 2.7x more tensor work per byte
+//                     staged than a pair-by-pair GEMM.  `tcgen05.mma.cta_group::1.kind::i8`, M=128, N=64, K=32.
+//   warps 2-5       : epilogue.  Thread <-> TMEM lane <-> output row: `tcgen05.ld` each S_g, convert, combine in
+//                     fp64 with the diagonal weights, apply the row/column scales, store 512 contiguous bytes.
+// Tiles are visited in an L2-friendly static order (groups of 8 row-tiles sweep the column tiles from the longest
+// k-range to the shortest); all three roles derive the same sequence from blockIdx, so no tile broadcast is needed.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace mcacq {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;  // BK in bytes (= int8 elements): one SWIZZLE_64B row
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_MAXG = 7;
+constexpr int OZ_GROUP_M = 8;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void oz_mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nOZ_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra OZ_DONE;\nbra OZ_WAIT;\nOZ_DONE:\n}"
+               ::"r"(oz_smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint64_t oz_desc(const void* smem_ptr) {
+  // K-major operand tile, SWIZZLE_64B: stride between 8-row groups = 512 B; descriptor version 1 (sm_100)
+  uint64_t d = (uint64_t)((oz_smem_u32(smem_ptr) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__device__ __forceinline__ void oz_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+
+struct OzTile { int64_t mt; int nt; int kb0, kb1; };
+
+// i-th tile of this CTA in the static order; returns false past the end
+__device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, OzTile& o) {
+  if (t >= m_tiles * n_tiles) return false;
+  const int64_t group_sz = (int64_t)OZ_GROUP_M * n_tiles;
+  const int64_t grp = t / group_sz;
+  const int64_t m0 = grp * OZ_GROUP_M;
+  const int64_t rows = (m_tiles - m0 < OZ_GROUP_M) ? (m_tiles - m0) : OZ_GROUP_M;
+  const int64_t within = t - grp * group_sz;
+  const int nrank = (int)(within / rows);
+  o.mt = m0 + within % rows;
+  o.nt = (tri_mode == MCACQ_TRI_LOWER) ? nrank : n_tiles - 1 - nrank;
+  o.kb0 = 0; o.kb1 = k_blocks;
+  if (tri_mode == MCACQ_TRI_UPPER) { int e = o.nt + 1; o.kb1 = e < k_blocks ? e : k_blocks; }     // k < (nt+1)*64
+  else if (tri_mode == MCACQ_TRI_LOWER) { o.kb0 = o.nt < k_blocks ? o.nt : k_blocks; }             // k >= nt*64
+  return true;
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
+                  int64_t M, int N, int K, int G, const double* __restrict__ row_scale, const double* __restrict__ col_scale,
+                  double* __restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = G * (OZ_A_TILE + OZ_B_TILE);
+  __shared__ __align__(8) uint64_t full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double s_col[OZ_BN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
+  const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
+  const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_STAGES; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int64_t it = 0;  // k-block counter across tiles
+      OzTile tl;
+      for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x) {
+        const int row0 = (int)(tl.mt * OZ_BM), col0 = tl.nt * OZ_BN;
+        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
+          const int s = (int)(it % OZ_STAGES);
+          if (it >= OZ_STAGES) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / OZ_STAGES) - 1) & 1));
+          oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
+          for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      int64_t it = 0, tile_i = 0;
+      OzTile tl;
+      for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
+        if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
+          oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
+          const int s = (int)(it % OZ_STAGES);
+          oz_mbar_wait(&full_bar[s], (uint32_t)((it / OZ_STAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint8_t* st = smem + (size_t)s * stage_bytes;
+          const bool first = (kb == tl.kb0);
+          for (int g = 0; g < G; g++) {
+            const uint32_t d = tmem_base + (uint32_t)(g * OZ_BN);
+            for (int p = 0; p <= g; p++) {
+              const uint64_t ad = oz_desc(st + p * OZ_A_TILE);
+              const uint64_t bd = oz_desc(st + G * OZ_A_TILE + (g - p) * OZ_B_TILE);
+#pragma unroll
+              for (int k = 0; k < OZ_BK / 32; k++)
+                oz_umma(d, ad + 2 * k, bd + 2 * k, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
+            }
+          }
+          oz_commit(&empty_bar[s]);
+        }
+        oz_commit(&acc_full);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int lg = warp & 3;                  // TMEM lane group this warp may access
+    const int r_in_tile = lg * 32 + lane;
+    const int etid = tid - 64;                // 0..127
+    int64_t tile_i = 0;
+    OzTile tl;
+    for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
+      const int64_t row = tl.mt * OZ_BM + r_in_tile;
+      const int col0 = tl.nt * OZ_BN;
+      // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
+      if (etid < OZ_BN) s_col[etid] = (col0 + etid < N) ? col_scale[col0 + etid] : 0.0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      double acc[OZ_BN];
+#pragma unroll
+      for (int c = 0; c < OZ_BN; c++) acc[c] = 0.0;
+      if (tl.kb1 > tl.kb0) {
+        oz_mbar_wait(&acc_full, (uint32_t)(tile_i & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        double w = 1.0 / 16384.0;  // 128^-2
+        for (int g = 0; g < G; g++) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN);
+#pragma unroll
+          for (int c = 0; c < OZ_BN; c += 32) {
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr + c));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[c + j] = fma(w, (double)(int32_t)v[j], acc[c + j]);
+          }
+          w *= (1.0 / 128.0);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive(&acc_empty);
+      } else {
+        // empty k-range (cannot happen for the triangular factors, kept for dense corner cases): still hand the
+        // accumulators back so the MMA thread's phase bookkeeping stays aligned
+        if (lane == 0) oz_mbar_arrive(&acc_empty);
+      }
+      if (row < M) {
+        const double rs = row_scale[row];
+        double* dst = C + row * ldc + col0;
+        if (col0 + OZ_BN <= N && (ldc & 1) == 0) {
+#pragma unroll
+          for (int c = 0; c < OZ_BN; c += 2)
+            *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c] * rs * s_col[c], acc[c + 1] * rs * s_col[c + 1]);
+        } else {
+          for (int c = 0; c < OZ_BN; c++) if (col0 + c < N) dst[c] = acc[c] * rs * s_col[c];
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // s_col reuse
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ---- slicing ------------------------------------------------------------------------------------------------------
+// X[rows x K] (fp64, pitch ldx) -> G int8 slices [G][rows][Kp] (Kp = slice pitch >= K, zero padded) and the row scale
+// 2^e with |x| 2^-e < 1.  fixed_exp != INT_MIN: use that exponent for every row (K(X, X_train) <= outputscale).
+__global__ void __launch_bounds__(256)
+slice_rows_kernel(const double* __restrict__ X, int64_t rows, int K, int64_t ldx, int Kp, int G, int fixed_exp,
+                  int8_t* __restrict__ S, double* __restrict__ scale) {
+  const int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  const double* x = X + row * ldx;
+  __shared__ double s_red[8];
+  __shared__ int s_exp;
+  int e;
+  if (fixed_exp != INT_MIN) {
+    e = fixed_exp;
+  } else {
+    double mx = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(x[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int w = 0; w < 8; w++) m = fmax(m, s_red[w]);
+      int ex = 0;
+      if (m > 0.0 && isfinite(m)) { frexp(m, &ex); }  // m = f * 2^ex, f in [0.5, 1)  =>  m * 2^-ex < 1
+      s_exp = ex;
+    }
+    __syncthreads();
+    e = s_exp;
+  }
+  if (threadIdx.x == 0) scale[row] = ldexp(1.0, e);
+  const size_t slice_stride = (size_t)rows * Kp;
+  int8_t* out = S + row * (size_t)Kp;
+  for (int k = threadIdx.x; k < Kp; k += 256) {
+    double r = (k < K) ? ldexp(x[k], -e) : 0.0;
+    for (int p = 0; p < G; p++) {
+      r *= 128.0;
+      const double qv = trunc(r);
+      out[p * slice_stride + k] = (int8_t)(int)qv;
+      r -= qv;
+    }
+  }
+}
+
+typedef CUresult (*OzEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static OzEncodeFn oz_encode_fn() {
+  static OzEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (OzEncodeFn)p;
+  }
+  return fn;
+}
+
+static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_t rows, uint64_t kbytes, uint64_t pitch,
+                       uint32_t box_rows) {
+  OzEncodeFn enc = oz_encode_fn();
+  if (!enc) return MCACQ_EINVAL;
+  cuuint64_t dims[3] = {kbytes, rows, slices};
+  cuuint64_t strides[2] = {pitch, pitch * rows};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
+}
+
+}  // namespace mcacq
+
+extern "C" int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, int G, int use_fixed_exp,
+                                int fixed_exp, int8_t* slices, double* row_scale, void* stream) {
+  using namespace mcacq;
+  if (!X || !slices || !row_scale || rows < 0 || K <= 0 || Kp < K || ldx < K || G <= 0 || G > OZ_MAXG) return MCACQ_EINVAL;
+  if (rows == 0) return 0;
+  slice_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(X, rows, K, ldx, Kp, G,
+                                                                       use_fixed_exp ? fixed_exp : INT_MIN, slices, row_scale);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G, const int8_t* A_slices,
+                                    const double* row_scale, const int8_t* B_slices, const double* col_scale, double* C,
+                                    int64_t ldc, void* stream) {
+  using namespace mcacq;
+  if (!A_slices || !B_slices || !row_scale || !col_scale || !C || M < 0 || N <= 0 || K <= 0 || ldc < N) return MCACQ_EINVAL;
+  if (G <= 0 || G > OZ_MAXG || (K % 16) != 0 || tri_mode < 0 || tri_mode > 2) return MCACQ_EINVAL;
+  if ((int64_t)K * 127 * 127 * G >= (int64_t)1 << 31) return MCACQ_ELIMIT;  // exact int32 accumulation of a diagonal
+  if (M == 0) return 0;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM))) return rc;
+  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, OZ_BN))) return rc;
+  static int sms = 0;
+  const size_t smem = (size_t)OZ_STAGES * OZ_MAXG * (OZ_A_TILE + OZ_B_TILE) + 1024;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { sms = 0; return (int)e; }
+  }
+  const int64_t tiles = ((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  ozaki_imma_kernel<<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, row_scale, col_scale, C, ldc);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}

@@ -122,6 +122,17 @@ int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A, const doub
 int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
                    double* C, int64_t ldc, int32_t* tile_counter, void* stream);
 
+/* ---- FP64-accurate contraction on the INT8 tensor cores (Ozaki-style splitting; csrc/ozaki_imma.cu) -------------
+ * Optional replacement of mcacq_dgemm_tri for `test_train_covar @ covar_cache`:
+ *   mcacq_slice_rows    : X[rows x K] (fp64) -> G signed 7-bit slices [G][rows][Kp] (int8) + row scale 2^e;
+ *   mcacq_ozaki_contract: C[M x N] = 2^(ea+fb) * sum_{p+q<G} 128^-(p+q+2) A_p B_q^T  (tcgen05 kind::i8, exact int32
+ *                         slice products, fp64 recombination); B slices are given as rows [N x K] (K contiguous).
+ * tri_mode as in mcacq_dgemm_tri (which k-range of B^T is non-zero).                                              */
+int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, int G, int use_fixed_exp, int fixed_exp,
+                     int8_t* slices, double* row_scale, void* stream);
+int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G, const int8_t* A_slices, const double* row_scale,
+                         const int8_t* B_slices, const double* col_scale, double* C, int64_t ldc, void* stream);
+
 size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
 
 /* Posterior over b q-batches: mean [b x q], covar [b x q x q] on the original outcome scale. */
