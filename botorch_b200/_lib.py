@@ -36,6 +36,8 @@ class Model(C.Structure):
         ("outputscale", C.c_double), ("mean_const", C.c_double), ("y_mean", C.c_double), ("y_std", C.c_double),
         ("x_offset", C.c_void_p), ("x_coef", C.c_void_p), ("lengthscale", C.c_void_p), ("U_train", C.c_void_p),
         ("alpha", C.c_void_p), ("R", C.c_void_p), ("Rt", C.c_void_p),
+        ("contraction", C.c_int32), ("g_fwd", C.c_int32), ("g_bwd", C.c_int32), ("_pad", C.c_int32),
+        ("Rt_slices", C.c_void_p), ("Rt_scale", C.c_void_p), ("R_slices", C.c_void_p), ("R_scale", C.c_void_p),
     ]
 
 

@@ -12,6 +12,7 @@
 //   dKt = dA R^T    (into the Kt buffer)    dgemm_tri_kernel (lower)          <- dominant FLOPs
 //   dU += sum_k (dKt + s*gmean*alpha) dk/du cov_cross_bwd_kernel
 //   dX  = dU / (coef * lengthscale)         unscale_grad_kernel
+#include <cmath>
 #include "common.cuh"
 
 namespace mcacq {
@@ -31,14 +32,15 @@ int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 
 struct Workspace {
-  double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU;
+  double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale;
+  int8_t* slices;
   int32_t* counter;
   size_t bytes;
 };
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static Workspace carve(void* base, int64_t b, int q, int d, int np, int r) {
+static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int int8_mode = 1) {
   Workspace w;
   char* p = (char*)base;
   size_t off = 0;
@@ -62,6 +64,9 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r) {
   w.gSxb = (double*)take((size_t)M * (r > 0 ? r : 1) * 8);
   w.row_scale = (double*)take((size_t)M * 8);
   w.dU = (double*)take((size_t)M * d * 8);
+  // operands of the optional INT8 contraction: 7 slices of the M x np left operand + its row scales
+  w.slice_scale = (double*)take((size_t)M * 8);
+  w.slices = (int8_t*)take(int8_mode ? (size_t)7 * M * np : 256);
   w.bytes = off;
   return w;
 }
@@ -72,6 +77,11 @@ static int check_model(const mcacq_model* m) {
   if (m->d > MCACQ_MAX_D) return MCACQ_ELIMIT;
   if (!m->x_offset || !m->x_coef || !m->lengthscale || !m->U_train || !m->alpha || !m->R || !m->Rt) return MCACQ_EINVAL;
   if (m->kernel_id != MCACQ_KERNEL_RBF && m->kernel_id != MCACQ_KERNEL_MATERN52) return MCACQ_EINVAL;
+  if (m->contraction != 0 && m->contraction != 1) return MCACQ_EINVAL;
+  if (m->contraction == 1) {
+    if (!m->Rt_slices || !m->Rt_scale || !m->R_slices || !m->R_scale) return MCACQ_EINVAL;
+    if (m->g_fwd < 1 || m->g_fwd > 7 || m->g_bwd < 1 || m->g_bwd > 7) return MCACQ_EINVAL;
+  }
   return 0;
 }
 
@@ -83,7 +93,17 @@ static int run_posterior_stage(const mcacq_model* m, const mcacq_baseline* base,
   int rc;
   if ((rc = mcacq_scale_inputs(X, M, m->d, m->x_offset, m->x_coef, m->lengthscale, w.U, st))) return rc;
   if ((rc = mcacq_cov_cross(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, w.Kt, m->np, st))) return rc;
-  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_UPPER, M, m->np, w.Kt, m->R, w.A, w.counter, st))) return rc;
+  if (m->contraction == 1) {
+    // Kt in (0, outputscale]: one fixed exponent for all rows, 2^e > outputscale
+    int e = 0;
+    frexp(m->outputscale, &e);
+    if ((rc = mcacq_slice_rows(w.Kt, M, m->np, m->np, m->np, m->g_fwd, 1, e, w.slices, w.slice_scale, st))) return rc;
+    if ((rc = mcacq_ozaki_contract(MCACQ_TRI_UPPER, M, m->np, m->np, m->g_fwd, w.slices, w.slice_scale, m->Rt_slices,
+                                   m->Rt_scale, w.A, m->np, st)))
+      return rc;
+  } else {
+    if ((rc = mcacq_dgemm_tri(MCACQ_TRI_UPPER, M, m->np, w.Kt, m->R, w.A, w.counter, st))) return rc;
+  }
   BlocksParams bp;
   bp.b = b; bp.q = q; bp.d = m->d; bp.np = m->np; bp.r = r;
   bp.kernel_id = m->kernel_id; bp.outputscale = m->outputscale; bp.mean_const = m->mean_const;
@@ -148,7 +168,15 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   bp.gmean = gmean; bp.gSxx = gSxx; bp.gSxb = gSxb;
   bp.row_scale = w.row_scale; bp.dU = w.dU;
   if ((rc = posterior_blocks_bwd(bp, st))) return rc;
-  if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
+  if (model->contraction == 1) {
+    if ((rc = mcacq_slice_rows(w.A, M, model->np, model->np, model->np, model->g_bwd, 0, 0, w.slices, w.slice_scale, st)))
+      return rc;
+    if ((rc = mcacq_ozaki_contract(MCACQ_TRI_LOWER, M, model->np, model->np, model->g_bwd, w.slices, w.slice_scale,
+                                   model->R_slices, model->R_scale, w.Kt, model->np, st)))
+      return rc;
+  } else {
+    if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
+  }
   if ((rc = mcacq_cov_cross_bwd(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
                                 model->np, w.row_scale, model->alpha, w.dU, /*accumulate=*/1, st)))
     return rc;

@@ -12,25 +12,28 @@
 //
 // Kernel structure (one persistent CTA per SM, 6 warps):
 //   warp 0 / lane 0 : TMA producer.  Per 64-byte k-block it loads G A-tiles (128 rows x 64 B) and G B-tiles
-//                     (64 rows x 64 B), SWIZZLE_64B, into a 2-stage ring (84 KB per stage at G = 7).
+//                     (64 rows x 64 B), SWIZZLE_64B, into a ring of 12*G KB stages (2 stages at G = 7, 3 at G <= 6;
+//                     32-byte k-blocks with a 5-deep ring measured 25% slower).
 //   warp 1 / lane 0 : MMA issuer.  All G diagonals S_g live in TMEM at once (G x 64 columns of int32, 448 of 512),
 //                     so one k-block of operands feeds G(G+1)/2 slice products: 2.7x more tensor work per byte
-//                     staged than a pair-by-pair GEMM.  `tcgen05.mma.cta_group::1.kind::i8`, M=128, N=64, K=32.
+//                     staged than a pair-by-pair GEMM.  Because S_p .. S_{G-1} are adjacent TMEM column ranges,
+//                     A_p x [B_0; ..; B_{G-1-p}] is issued as ONE wide `tcgen05.mma.cta_group::1.kind::i8`
+//                     (M=128, N<=256, K=32): 10 instructions per K step at G = 7 instead of 28.
 //   warps 2-5       : epilogue.  Thread <-> TMEM lane <-> output row: `tcgen05.ld` each S_g, convert, combine in
 //                     fp64 with the diagonal weights, apply the row/column scales, store 512 contiguous bytes.
 // Tiles are visited in an L2-friendly static order (groups of 8 row-tiles sweep the column tiles from the longest
 // k-range to the shortest); all three roles derive the same sequence from blockIdx, so no tile broadcast is needed.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mcacq {
 
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;  // BK in bytes (= int8 elements): one SWIZZLE_64B row
-constexpr int OZ_STAGES = 2;
+constexpr int OZ_BM = 128, OZ_BN = 64;  // BK (bytes = int8 elements) is a template parameter: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+constexpr int OZ_MAX_STAGES = 4;                    // ring depth is chosen at run time: as many 12*G KB stages as fit
 constexpr int OZ_MAXG = 7;
 constexpr int OZ_GROUP_M = 8;
 constexpr int OZ_THREADS = 192;
-constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void oz_mbar_init(uint64_t* b, int count) {
@@ -50,12 +53,13 @@ __device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uin
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+template <int OZ_BK>
 __device__ __forceinline__ uint64_t oz_desc(const void* smem_ptr) {
-  // K-major operand tile, SWIZZLE_64B: stride between 8-row groups = 512 B; descriptor version 1 (sm_100)
+  // K-major operand tile, SWIZZLE_64B / 128B: stride between 8-row groups = 8 * BK bytes; descriptor version 1 (sm_100)
   uint64_t d = (uint64_t)((oz_smem_u32(smem_ptr) & 0x3FFFF) >> 4);
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)((8 * OZ_BK) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
+  d |= (uint64_t)(OZ_BK == 128 ? 2 : 4) << 61;
   return d;
 }
 __device__ __forceinline__ void oz_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -69,6 +73,7 @@ __device__ __forceinline__ void oz_commit(uint64_t* bar) {
 struct OzTile { int64_t mt; int nt; int kb0, kb1; };
 
 // i-th tile of this CTA in the static order; returns false past the end
+template <int OZ_BK>
 __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, OzTile& o) {
   if (t >= m_tiles * n_tiles) return false;
   const int64_t group_sz = (int64_t)OZ_GROUP_M * n_tiles;
@@ -80,19 +85,21 @@ __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles,
   o.mt = m0 + within % rows;
   o.nt = (tri_mode == MCACQ_TRI_LOWER) ? nrank : n_tiles - 1 - nrank;
   o.kb0 = 0; o.kb1 = k_blocks;
-  if (tri_mode == MCACQ_TRI_UPPER) { int e = o.nt + 1; o.kb1 = e < k_blocks ? e : k_blocks; }     // k < (nt+1)*64
-  else if (tri_mode == MCACQ_TRI_LOWER) { o.kb0 = o.nt < k_blocks ? o.nt : k_blocks; }             // k >= nt*64
+  if (tri_mode == MCACQ_TRI_UPPER) { int e = ((o.nt + 1) * OZ_BN + OZ_BK - 1) / OZ_BK; o.kb1 = e < k_blocks ? e : k_blocks; }  // k < (nt+1)*BN
+  else if (tri_mode == MCACQ_TRI_LOWER) { int b = (o.nt * OZ_BN) / OZ_BK; o.kb0 = b < k_blocks ? b : k_blocks; }              // k >= nt*BN
   return true;
 }
 
+template <int OZ_BK>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
-                  int64_t M, int N, int K, int G, const double* __restrict__ row_scale, const double* __restrict__ col_scale,
-                  double* __restrict__ C, int64_t ldc) {
+                  int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
+                  const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
   const int stage_bytes = G * (OZ_A_TILE + OZ_B_TILE);
-  __shared__ __align__(8) uint64_t full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
+  __shared__ __align__(8) uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ double s_col[OZ_BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,7 +108,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
 
   if (tid == 0) {
-    for (int s = 0; s < OZ_STAGES; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < stages; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
     oz_mbar_init(&acc_full, 1);
     oz_mbar_init(&acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -120,11 +127,11 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // ================= TMA producer =================
       int64_t it = 0;  // k-block counter across tiles
       OzTile tl;
-      for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x) {
+      for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x) {
         const int row0 = (int)(tl.mt * OZ_BM), col0 = tl.nt * OZ_BN;
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
-          const int s = (int)(it % OZ_STAGES);
-          if (it >= OZ_STAGES) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / OZ_STAGES) - 1) & 1));
+          const int s = (int)(it % stages);
+          if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
           oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + (size_t)s * stage_bytes;
           for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
@@ -135,28 +142,35 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer =================
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      // instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128; N is filled in per instruction
+      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       int64_t it = 0, tile_i = 0;
       OzTile tl;
-      for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
+      for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
         if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
           oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
-          const int s = (int)(it % OZ_STAGES);
-          oz_mbar_wait(&full_bar[s], (uint32_t)((it / OZ_STAGES) & 1));
+          const int s = (int)(it % stages);
+          oz_mbar_wait(&full_bar[s], (uint32_t)((it / stages) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint8_t* st = smem + (size_t)s * stage_bytes;
           const bool first = (kb == tl.kb0);
-          for (int g = 0; g < G; g++) {
-            const uint32_t d = tmem_base + (uint32_t)(g * OZ_BN);
-            for (int p = 0; p <= g; p++) {
-              const uint64_t ad = oz_desc(st + p * OZ_A_TILE);
-              const uint64_t bd = oz_desc(st + G * OZ_A_TILE + (g - p) * OZ_B_TILE);
+          // A_p times the stacked tiles [B_0; ...; B_{G-1-p}] lands in the consecutive accumulators g = p .. G-1, so the
+          // G(G+1)/2 slice products of a K=32 step are issued as wide UMMAs (N up to 256) instead of G(G+1)/2 N=64 ones:
+          // the A tile is read from shared memory once per p, not once per pair.
 #pragma unroll
-              for (int k = 0; k < OZ_BK / 32; k++)
-                oz_umma(d, ad + 2 * k, bd + 2 * k, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
+          for (int k = 0; k < OZ_BK / 32; k++) {
+            for (int p = 0; p < G; p++) {
+              const uint64_t ad = oz_desc<OZ_BK>(st + p * OZ_A_TILE) + 2 * k;
+              const int ncols = (G - p) * OZ_BN;
+              for (int c0 = 0; c0 < ncols; c0 += 256) {
+                const int nn = (ncols - c0 < 256) ? (ncols - c0) : 256;
+                const uint64_t bd = oz_desc<OZ_BK>(st + G * OZ_A_TILE + (c0 / OZ_BN) * OZ_B_TILE) + 2 * k;
+                const uint32_t idesc_n = idesc_base | ((uint32_t)(nn >> 3) << 17);
+                oz_umma(tmem_base + (uint32_t)(p * OZ_BN + c0), ad, bd, idesc_n, (first && p == 0 && k == 0) ? 0u : 1u);
+              }
             }
           }
           oz_commit(&empty_bar[s]);
@@ -171,7 +185,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int etid = tid - 64;                // 0..127
     int64_t tile_i = 0;
     OzTile tl;
-    for (int64_t t = blockIdx.x; oz_tile(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
+    for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
       const int64_t row = tl.mt * OZ_BM + r_in_tile;
       const int col0 = tl.nt * OZ_BN;
       // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
@@ -288,7 +302,7 @@ static OzEncodeFn oz_encode_fn() {
 }
 
 static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_t rows, uint64_t kbytes, uint64_t pitch,
-                       uint32_t box_rows) {
+                       uint32_t box_rows, int OZ_BK) {
   OzEncodeFn enc = oz_encode_fn();
   if (!enc) return MCACQ_EINVAL;
   cuuint64_t dims[3] = {kbytes, rows, slices};
@@ -296,7 +310,8 @@ static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_
   cuuint32_t box[3] = {(cuuint32_t)OZ_BK, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, OZ_BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
 }
@@ -323,22 +338,34 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   if (G <= 0 || G > OZ_MAXG || (K % 16) != 0 || tri_mode < 0 || tri_mode > 2) return MCACQ_EINVAL;
   if ((int64_t)K * 127 * 127 * G >= (int64_t)1 << 31) return MCACQ_ELIMIT;  // exact int32 accumulation of a diagonal
   if (M == 0) return 0;
+  // 128-byte k-blocks (full L2 lines, SWIZZLE_128B) when at least two stages of them fit, else 64-byte k-blocks
+  const size_t smem_budget = 232448 - 2048 - 1024;  // 227 KB per CTA minus static shared memory and alignment slack
+  int bk = (getenv("MCACQ_OZ_BK") != nullptr) ? atoi(getenv("MCACQ_OZ_BK")) : 0;
+  if (bk != 64 && bk != 128) bk = ((size_t)2 * G * (OZ_BM + OZ_BN) * 128 <= smem_budget) ? 128 : 64;
+  const size_t stage_bytes = (size_t)G * (OZ_BM + OZ_BN) * bk;
+  int stages = (int)(smem_budget / stage_bytes);
+  if (stages > OZ_MAX_STAGES) stages = OZ_MAX_STAGES;
+  if (stages < 1) return MCACQ_ELIMIT;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
   CUtensorMap mapA, mapB;
   int rc;
-  if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM))) return rc;
-  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, OZ_BN))) return rc;
+  if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk))) return rc;
+  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, OZ_BN, bk))) return rc;
   static int sms = 0;
-  const size_t smem = (size_t)OZ_STAGES * OZ_MAXG * (OZ_A_TILE + OZ_B_TILE) + 1024;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_imma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ozaki_imma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
     if (e != cudaSuccess) { sms = 0; return (int)e; }
   }
   const int64_t tiles = ((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  ozaki_imma_kernel<<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, row_scale, col_scale, C, ldc);
+  if (bk == 128)
+    ozaki_imma_kernel<128><<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
+  else
+    ozaki_imma_kernel<64><<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

@@ -15,7 +15,7 @@ import torch
 from torch import Tensor
 from torch.nn import Module
 
-from .. import _lib
+from .. import _lib, settings
 from ..exceptions.errors import InputDataError, UnsupportedError
 from ..exceptions.warnings import InputDataWarning
 from ..posteriors.gpytorch import GPyTorchPosterior, MultivariateNormal
@@ -131,7 +131,7 @@ class SingleTaskGP(Model):
         if isinstance(self.covar_module, ScaleKernel):
             vals.append(self.covar_module.outputscale.detach().reshape(-1))
         flat = torch.cat([v.to("cpu", torch.float64) for v in vals])
-        return (self.train_inputs[0].device, tuple(flat.tolist()))
+        return (self.train_inputs[0].device, settings.contraction.value(), tuple(flat.tolist()))
 
     def _base_kernel(self) -> Kernel:
         k = self.covar_module.base_kernel if isinstance(self.covar_module, ScaleKernel) else self.covar_module
@@ -164,7 +164,8 @@ class SingleTaskGP(Model):
         self._strategy = DevicePredictionStrategy(
             train_X_transformed=Xt, train_Y_standardized=self.train_targets, lengthscale=ls.to(**f64),
             noise=self.likelihood.noise.detach().to(**f64), kernel_id=base.kernel_id, outputscale=outputscale,
-            mean_const=float(self.mean_module.constant.detach()), x_offset=offset, x_coef=coef, y_mean=y_mean, y_std=y_std)
+            mean_const=float(self.mean_module.constant.detach()), x_offset=offset, x_coef=coef, y_mean=y_mean, y_std=y_std,
+            contraction=settings.contraction.value())
         self._strategy_key = key
         return self._strategy
 

@@ -74,6 +74,16 @@ typedef struct {
   const double* alpha;       /* [np] mean_cache = (K + noise)^{-1} (y - c), zero padded     */
   const double* R;           /* [np x np] covar_cache = L^{-T}, upper triangular, zero padded */
   const double* Rt;          /* [np x np] transpose of R (lower triangular), zero padded    */
+  /* Optional INT8-tensor-core contraction (csrc/ozaki_imma.cu).  contraction = 0: FP64 DMMA (mcacq_dgemm_tri);
+   * contraction = 1: Ozaki split, g_fwd / g_bwd diagonals (7 / 6 keep 1e-9 on values / 1e-7 on gradients).      */
+  int32_t contraction;
+  int32_t g_fwd;
+  int32_t g_bwd;
+  int32_t _pad;
+  const int8_t* Rt_slices;   /* [7][np][np] row-scaled slices of R^T (row j = column j of R)  -- forward B operand */
+  const double* Rt_scale;    /* [np]                                                                             */
+  const int8_t* R_slices;    /* [7][np][np] row-scaled slices of R                            -- backward B operand */
+  const double* R_scale;     /* [np]                                                                             */
 } mcacq_model;
 
 /* qLogNEI baseline operands (acquisition/logei.py:393-459); r == 0 for qLogEI.             */

@@ -155,3 +155,29 @@ def test_mock_style_bounds_qlogei():
     assert ((vl.exp() - 1e3).abs() < 25).all()  # E[max_q y] is O(1) for Hartmann-6
     with pytest.raises(ValueError):
         qLogExpectedImprovement(model, best_f=0.0, tau_relu=-1.0)
+
+
+@pytest.mark.parametrize("cfg,n,b", [("C1", None, 64), ("C2", None, 40), ("C3", 1100, 24), ("C3", None, 64)])
+def test_int8_contraction_mode_parity(cfg, n, b):
+    """Same parity bar with the contraction on the INT8 tensor cores (Ozaki split, tcgen05): values 1e-9, grads 1e-7,
+    posterior mean/variance 1e-9."""
+    from botorch_b200 import settings
+    from oracle.acquisition import value_and_grad
+
+    with settings.contraction("int8"):
+        data, model, acqf, orc, X, dev = _setup(cfg, n=n, b=b)
+        assert model.prediction_strategy().contraction == "int8"
+        post = model.posterior(X.to(dev))
+        mean_o, cov_o = orc.gp.posterior_mvn(X)
+        var_o = cov_o.diagonal(dim1=-1, dim2=-2)
+        assert _rel(post.mean.squeeze(-1), mean_o) < RTOL
+        assert float(((post.variance.squeeze(-1).cpu() - var_o).abs() / var_o).max()) < RTOL
+        v_o, g_o = value_and_grad(orc, X)
+        Xg = X.to(dev).requires_grad_(True)
+        v = acqf(Xg)
+        (g,) = torch.autograd.grad(v.sum(), Xg)
+        assert float(((v.detach().cpu() - v_o).abs() / v_o.abs()).max()) < RTOL
+        assert _rel(g, g_o) < 1e-7
+        with torch.no_grad():  # chunk invariance holds in this mode too
+            full = acqf(X.to(dev))
+            assert torch.equal(full[: b // 2], acqf(X.to(dev)[: b // 2]))

@@ -9,6 +9,9 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 b = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0")
+import os
+from botorch_b200 import settings
+settings.contraction.set(os.environ.get("MCACQ_CONTRACTION", "dmma"))
 data = configs.make_problem(configs.CONFIGS[cfg])
 model = configs.build_model(data, dev)
 acqf = configs.build_acqf(data, model)
