@@ -53,6 +53,23 @@ __device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uin
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void oz_tma_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(oz_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 template <int OZ_BK>
 __device__ __forceinline__ uint64_t oz_desc(const void* smem_ptr) {
   // K-major operand tile, SWIZZLE_64B / 128B: stride between 8-row groups = 8 * BK bytes; descriptor version 1 (sm_100)
@@ -72,25 +89,30 @@ __device__ __forceinline__ void oz_commit(uint64_t* bar) {
 
 struct OzTile { int64_t mt; int nt; int kb0, kb1; };
 
-// i-th tile of this CTA in the static order; returns false past the end
-template <int OZ_BK>
+// t-th CLUSTER tile in the static order (a cluster tile = CM x CN adjacent CTA tiles that share operand loads);
+// returns false past the end.  The k-range is the union over the cluster's column tiles (the extra k-blocks of the
+// narrower columns multiply stored zeros of the triangular factor).
+template <int OZ_BK, int CM, int CN>
 __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, OzTile& o) {
-  if (t >= m_tiles * n_tiles) return false;
-  const int64_t group_sz = (int64_t)OZ_GROUP_M * n_tiles;
+  const int64_t cm_tiles = (m_tiles + CM - 1) / CM;
+  const int cn_tiles = (n_tiles + CN - 1) / CN;
+  if (t >= cm_tiles * cn_tiles) return false;
+  constexpr int GM = (OZ_GROUP_M / CM) > 0 ? (OZ_GROUP_M / CM) : 1;
+  const int64_t group_sz = (int64_t)GM * cn_tiles;
   const int64_t grp = t / group_sz;
-  const int64_t m0 = grp * OZ_GROUP_M;
-  const int64_t rows = (m_tiles - m0 < OZ_GROUP_M) ? (m_tiles - m0) : OZ_GROUP_M;
+  const int64_t m0 = grp * GM;
+  const int64_t rows = (cm_tiles - m0 < GM) ? (cm_tiles - m0) : GM;
   const int64_t within = t - grp * group_sz;
   const int nrank = (int)(within / rows);
-  o.mt = m0 + within % rows;
-  o.nt = (tri_mode == MCACQ_TRI_LOWER) ? nrank : n_tiles - 1 - nrank;
+  o.mt = m0 + within % rows;                                                   // cluster row-tile index
+  o.nt = (tri_mode == MCACQ_TRI_LOWER) ? nrank : cn_tiles - 1 - nrank;           // cluster column-tile index
   o.kb0 = 0; o.kb1 = k_blocks;
-  if (tri_mode == MCACQ_TRI_UPPER) { int e = ((o.nt + 1) * OZ_BN + OZ_BK - 1) / OZ_BK; o.kb1 = e < k_blocks ? e : k_blocks; }  // k < (nt+1)*BN
-  else if (tri_mode == MCACQ_TRI_LOWER) { int b = (o.nt * OZ_BN) / OZ_BK; o.kb0 = b < k_blocks ? b : k_blocks; }              // k >= nt*BN
+  if (tri_mode == MCACQ_TRI_UPPER) { int e = ((o.nt + 1) * CN * OZ_BN + OZ_BK - 1) / OZ_BK; o.kb1 = e < k_blocks ? e : k_blocks; }
+  else if (tri_mode == MCACQ_TRI_LOWER) { int b = (o.nt * CN * OZ_BN) / OZ_BK; o.kb0 = b < k_blocks ? b : k_blocks; }
   return true;
 }
 
-template <int OZ_BK>
+template <int OZ_BK, int CM, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
                   int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
@@ -107,8 +129,20 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
   const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
 
+  // position inside the cluster: CTAs of one cluster row share the A tiles, CTAs of one cluster column the B tiles
+  constexpr int CSIZE = CM * CN;
+  const uint32_t crank = (CSIZE > 1) ? oz_cluster_rank() : 0u;
+  const int rm = (int)crank / CN, rn = (int)crank % CN;
+  const uint16_t row_mask = (uint16_t)(((1u << CN) - 1u) << (rm * CN));
+  uint16_t col_mask = 0;
+#pragma unroll
+  for (int i = 0; i < CM; i++) col_mask |= (uint16_t)(1u << (i * CN + rn));
+  const uint16_t release_mask = row_mask | col_mask;   // the CTAs that write into this CTA's ring (and vice versa)
+  const int64_t cluster_id = blockIdx.x / CSIZE;
+  const int64_t num_clusters = gridDim.x / CSIZE;
+
   if (tid == 0) {
-    for (int s = 0; s < stages; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < stages; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], CM + CN - 1); }
     oz_mbar_init(&acc_full, 1);
     oz_mbar_init(&acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,6 +153,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CSIZE > 1) oz_cluster_sync();   // every CTA's barriers exist before any peer multicasts into it
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
@@ -127,15 +162,21 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // ================= TMA producer =================
       int64_t it = 0;  // k-block counter across tiles
       OzTile tl;
-      for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x) {
-        const int row0 = (int)(tl.mt * OZ_BM), col0 = tl.nt * OZ_BN;
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters) {
+        const int row0 = (int)((tl.mt * CM + rm) * OZ_BM), col0 = (tl.nt * CN + rn) * OZ_BN;
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
           const int s = (int)(it % stages);
           if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
           oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + (size_t)s * stage_bytes;
-          for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
-          for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
+          if (CSIZE == 1) {
+            for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
+            for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
+          } else {
+            // each CTA fetches 1/CN of its row's A slices and 1/CM of its column's B slices and multicasts them
+            for (int p = rn; p < G; p += CN) oz_tma_3d_mc(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p, row_mask);
+            for (int q = rm; q < G; q += CM) oz_tma_3d_mc(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, col_mask);
+          }
         }
       }
     }
@@ -146,7 +187,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       int64_t it = 0, tile_i = 0;
       OzTile tl;
-      for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
         if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
           oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -173,7 +214,8 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               }
             }
           }
-          oz_commit(&empty_bar[s]);
+          if (CSIZE == 1) oz_commit(&empty_bar[s]);
+          else oz_commit_mc(&empty_bar[s], release_mask);
         }
         oz_commit(&acc_full);
       }
@@ -185,9 +227,9 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int etid = tid - 64;                // 0..127
     int64_t tile_i = 0;
     OzTile tl;
-    for (int64_t t = blockIdx.x; oz_tile<OZ_BK>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += gridDim.x, tile_i++) {
-      const int64_t row = tl.mt * OZ_BM + r_in_tile;
-      const int col0 = tl.nt * OZ_BN;
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
+      const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
+      const int col0 = (tl.nt * CN + rn) * OZ_BN;
       // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
       if (etid < OZ_BN) s_col[etid] = (col0 + etid < N) ? col_scale[col0 + etid] : 0.0;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -223,7 +265,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // accumulators back so the MMA thread's phase bookkeeping stays aligned
         if (lane == 0) oz_mbar_arrive(&acc_empty);
       }
-      if (row < M) {
+      if (row < M && col0 < N) {
         const double rs = row_scale[row];
         double* dst = C + row * ldc + col0;
         if (col0 + OZ_BN <= N && (ldc & 1) == 0) {
@@ -239,6 +281,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CSIZE > 1) oz_cluster_sync();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
@@ -316,6 +359,61 @@ static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_
   return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
 }
 
+template <int BKB, int CM, int CN>
+static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M, int N, int K, int G,
+                       int stages, size_t smem, size_t smem_budget, const double* row_scale, const double* col_scale,
+                       double* C, int64_t ldc, cudaStream_t st) {
+  auto kern = ozaki_imma_kernel<BKB, CM, CN>;
+  static int max_clusters = -1;
+  constexpr int CS = CM * CN;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CS > 1) ? 1 : 0;
+  if (max_clusters < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (CS > 1) {
+      cfg.gridDim = dim3(sms / CS * CS);
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return e != cudaSuccess ? (int)e : MCACQ_ELIMIT; }
+      max_clusters = n;
+    } else {
+      max_clusters = sms;
+    }
+  }
+  const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
+  const int64_t n_tiles = (N + OZ_BN - 1) / OZ_BN;
+  const int64_t ctiles = ((m_tiles + CM - 1) / CM) * ((n_tiles + CN - 1) / CN);
+  const int nclusters = (int)(ctiles < max_clusters ? ctiles : max_clusters);
+  cfg.gridDim = dim3(nclusters * CS);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
+  count_launch();
+  if (e != cudaSuccess) return (int)e;
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+static int oz_launch(int bk, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M,
+                     int N, int K, int G, int stages, size_t smem, size_t smem_budget, const double* row_scale,
+                     const double* col_scale, double* C, int64_t ldc, cudaStream_t st) {
+#define OZ_CASE(B, A_, C_) if (bk == B && cm == A_ && cn == C_) \
+    return oz_launch_t<B, A_, C_>(mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc, st);
+  OZ_CASE(64, 1, 1) OZ_CASE(64, 2, 2) OZ_CASE(64, 1, 4) OZ_CASE(64, 2, 4) OZ_CASE(64, 2, 1) OZ_CASE(64, 1, 2) OZ_CASE(64, 4, 2)
+  OZ_CASE(128, 1, 1) OZ_CASE(128, 2, 2) OZ_CASE(128, 1, 4) OZ_CASE(128, 2, 4)
+#undef OZ_CASE
+  return MCACQ_EINVAL;
+}
+
 }  // namespace mcacq
 
 extern "C" int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, int G, int use_fixed_exp,
@@ -351,22 +449,11 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   int rc;
   if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk))) return rc;
   if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, OZ_BN, bk))) return rc;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_imma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ozaki_imma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
-    if (e != cudaSuccess) { sms = 0; return (int)e; }
-  }
-  const int64_t tiles = ((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  if (bk == 128)
-    ozaki_imma_kernel<128><<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
-  else
-    ozaki_imma_kernel<64><<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
-  count_launch();
-  MCACQ_CUDA_CHECK_LAUNCH();
-  return 0;
+  // Cluster shape (rows x columns of CTA tiles sharing operand loads through TMA multicast).  Measured on B200
+  // (profiles/r01_ozaki_int8.md): multicast halves the L2 reads but not the bytes delivered to each SM, which is what
+  // bounds this kernel (~20 B/clk/SM, ~5.8 TB/s chip-wide), so 1x1 is the default; 2x1 / 1x2 tie, 2x2 is 13% slower.
+  int cm = 1, cn = 1;
+  if (getenv("MCACQ_OZ_CLUSTER") != nullptr) { int v = atoi(getenv("MCACQ_OZ_CLUSTER")); cm = v / 10; cn = v % 10; }
+  return oz_launch(bk, cm, cn, mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
+                   (cudaStream_t)stream);
 }
