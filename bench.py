@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--raw-samples", type=int, default=None, help="override b (total q-batches per step)")
     ap.add_argument("--chunk", type=int, default=8192, help="q-batches per fused call (init_batch_limit analogue)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="q-batches in the CPU baseline sample")
+    ap.add_argument("--contraction", default="int8", choices=["int8", "dmma"],
+                    help="headline contraction mode: int8 = Ozaki split on the INT8 tensor cores (tcgen05), "
+                         "dmma = FP64 DMMA kernel; the other mode is measured too and reported under 'alt_mode'")
     return ap.parse_args()
 
 
@@ -133,37 +136,11 @@ def main():
     lo, hi = shard_bounds(b_total, rank, world)
     b_local = hi - lo
 
-    model = configs.build_model(data, dev)
-    acqf = configs.build_acqf(data, model)
+    from botorch_b200 import settings
+
     X_host = configs.eval_points(data, b_total)[lo:hi].contiguous().pin_memory()
     X_dev = X_host.to(dev)
     chunk = min(args.chunk, max(1, b_local))
-
-    def step_resident():
-        """fwd+bwd over the shard, inputs resident in HBM; returns (values, grads)."""
-        vals, grads = [], []
-        for i in range(0, b_local, chunk):
-            Xc = X_dev[i:i + chunk].detach().requires_grad_(True)
-            v = acqf(Xc)
-            (g,) = torch.autograd.grad(v.sum(), Xc)
-            vals.append(v.detach())
-            grads.append(g)
-        v = torch.cat(vals)
-        full = all_gather_values(v, b_total) if world > 1 else v
-        return full, grads
-
-    def step_e2e():
-        """Same through host buffers: H2D of X, D2H of values and gradient (what gen_candidates_scipy moves)."""
-        out_v = torch.empty(b_local, dtype=torch.float64).pin_memory()
-        out_g = torch.empty(b_local, spec.q, spec.d, dtype=torch.float64).pin_memory()
-        for i in range(0, b_local, chunk):
-            Xc = X_host[i:i + chunk].to(dev, non_blocking=True).requires_grad_(True)
-            v = acqf(Xc)
-            (g,) = torch.autograd.grad(v.sum(), Xc)
-            out_v[i:i + chunk].copy_(v.detach(), non_blocking=True)
-            out_g[i:i + chunk].copy_(g, non_blocking=True)
-        torch.cuda.synchronize()
-        return out_v, out_g
 
     def barrier():
         if world > 1:
@@ -183,47 +160,82 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    LaunchStats.launches = 0
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms_total = timed(step_resident, args.steps)
-    clock_info = clocks.stop()
-    launches = LaunchStats.launches
+    def measure(mode: str, with_clocks: bool):
+        """Build the model in the given contraction mode and time K resident steps and K host-buffer (e2e) steps."""
+        with settings.contraction(mode):
+            model = configs.build_model(data, dev)
+            acqf = configs.build_acqf(data, model)
+            model.prediction_strategy()
+
+            def step_resident():
+                vals = []
+                for i in range(0, b_local, chunk):
+                    Xc = X_dev[i:i + chunk].detach().requires_grad_(True)
+                    v = acqf(Xc)
+                    (g,) = torch.autograd.grad(v.sum(), Xc)
+                    vals.append(v.detach())
+                v = torch.cat(vals)
+                return all_gather_values(v, b_total) if world > 1 else v
+
+            def step_e2e():
+                out_v = torch.empty(b_local, dtype=torch.float64).pin_memory()
+                out_g = torch.empty(b_local, spec.q, spec.d, dtype=torch.float64).pin_memory()
+                for i in range(0, b_local, chunk):
+                    Xc = X_host[i:i + chunk].to(dev, non_blocking=True).requires_grad_(True)
+                    v = acqf(Xc)
+                    (g,) = torch.autograd.grad(v.sum(), Xc)
+                    out_v[i:i + chunk].copy_(v.detach(), non_blocking=True)
+                    out_g[i:i + chunk].copy_(g, non_blocking=True)
+                torch.cuda.synchronize()
+                return out_v, out_g
+
+            for _ in range(max(args.warmup, 3)):
+                step_resident()
+            LaunchStats.launches = 0
+            clocks = ClockSampler(local_rank) if with_clocks else None
+            if clocks:
+                clocks.start()
+            ms_total = timed(step_resident, args.steps)
+            clock_info = clocks.stop() if clocks else None
+            launches = LaunchStats.launches
+            for _ in range(2):
+                step_e2e()
+            ms_e2e = timed(step_e2e, args.steps)
+        return {"model": model, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "clocks": clock_info}
+
+    other = "dmma" if args.contraction == "int8" else "int8"
+    head = measure(args.contraction, with_clocks=True)
+    alt = measure(other, with_clocks=False)
+    model = head["model"]
+    ms_total, ms_e2e, launches, clock_info = head["ms_total"], head["ms_e2e"], head["launches"], head["clocks"]
     pts_per_step = b_total * spec.q * spec.S
     value = pts_per_step * args.steps / (ms_total * 1e-3)
-
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
     e2e_value = pts_per_step * args.steps / (ms_e2e * 1e-3)
 
     # ------------------------------------------------------------------ roofline of the dominant kernel (rank 0)
-    roofline, cpu_base = None, None
+    roofline, roofline_alt, cpu_base = None, None, None
     if rank == 0:
         strat = model.prediction_strategy()
         L = _lib.lib()
         M = chunk * spec.q
         f64 = dict(device=dev, dtype=torch.float64)
-        A = torch.randn(M, strat.np, **f64)
-        Cc = torch.empty(M, strat.np, **f64)
-        counter = torch.zeros(64, dtype=torch.int32, device=dev)
         st = _lib.stream_ptr()
-        durs = []
-        for it in range(3 + 2 * args.steps):
-            mode, Bm = (_lib.TRI_UPPER, strat.R) if it % 2 == 0 else (_lib.TRI_LOWER, strat.Rt)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            L.mcacq_dgemm_tri(mode, M, strat.np, A.data_ptr(), Bm.data_ptr(), Cc.data_ptr(), counter.data_ptr(), st)
-            e1.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                durs.append(e0.elapsed_time(e1))
-        avg_ms = sum(durs) / len(durs)
         alg_flops = float(M) * strat.np * (strat.np + 1)  # 2 * M * np*(np+1)/2: only the triangle of R is contracted
-        # FP64 peak: MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 tensor denominator is measured
-        # here with cuBLAS DGEMM 8192^3 (best of 5), as SURVEY.md section 8d prescribes.
+
+        def time_launch(fn, reps):
+            durs = []
+            for it in range(3 + reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(it)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    durs.append(e0.elapsed_time(e1))
+            return sum(durs) / len(durs)
+
+        # FP64 peak: MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 tensor denominator is measured here with
+        # cuBLAS DGEMM 8192^3 (best of 6), as SURVEY.md section 8d prescribes.
         a = torch.randn(8192, 8192, **f64)
         bmat = torch.randn(8192, 8192, **f64)
         best = 1e9
@@ -234,22 +246,64 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        peak_tf = 2.0 * 8192**3 / (best * 1e-3) * 1e-12
+        fp64_peak_tf = 2.0 * 8192**3 / (best * 1e-3) * 1e-12
         del a, bmat
-        achieved_tf = alg_flops / (avg_ms * 1e-3) * 1e-12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dgemm_tri_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(f"{spec.name}_chunk{chunk}")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "tensor", "kernel": "dgemm_tri_kernel (FP64 DMMA.8x8x4)", "achieved": achieved_tf,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        peak_src = "MEASURED_PEAKS.json" if "bf16_tflops" in peaks else "fallback 1.59 PF (B200_PROFILING.md)"
+
+        def dmma_roofline():
+            A = torch.randn(M, strat.np, **f64)
+            Cc = torch.empty(M, strat.np, **f64)
+            counter = torch.zeros(64, dtype=torch.int32, device=dev)
+
+            def fn(it):
+                mode, Bm = (_lib.TRI_UPPER, strat.R) if it % 2 == 0 else (_lib.TRI_LOWER, strat.Rt)
+                L.mcacq_dgemm_tri(mode, M, strat.np, A.data_ptr(), Bm.data_ptr(), Cc.data_ptr(), counter.data_ptr(), st)
+
+            ms = time_launch(fn, 2 * args.steps)
+            ach = alg_flops / (ms * 1e-3) * 1e-12
+            return {"bound": "tensor", "kernel": "dgemm_tri_kernel (FP64 DMMA.8x8x4)", "achieved": ach, "peak": fp64_peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / fp64_peak_tf, "traffic": 3.16e9 * (M / 16384.0),
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
-                                   "DMMA pipe microbenchmark: 37.2 TF/s, profiles/r01_ubench_fp64_pipe.txt)",
-                    "launch_ms": avg_ms, "alg_flops_per_launch": alg_flops,
-                    "step_alg_tflops": (2.0 * spec.q * spec.n * spec.n * b_total / world) / (ms_total / args.steps * 1e-3) * 1e-12}
+                                   "DMMA pipe microbenchmark 37.2 TF/s, profiles/r01_ubench_fp64_pipe.txt)",
+                    "launch_ms": ms, "alg_flops_per_launch": alg_flops,
+                    "traffic_source": "ncu dram__bytes_read+write at M=16384 scaled to this M (profiles/README.md)"}
+
+        def int8_roofline():
+            G = 7
+            pairs = G * (G + 1) // 2
+            A = torch.rand(M, strat.np, **f64)
+            sl = torch.empty(G, M, strat.np, dtype=torch.int8, device=dev)
+            rs = torch.empty(M, **f64)
+            L.mcacq_slice_rows(A.data_ptr(), M, strat.np, strat.np, strat.np, G, 1, 1, sl.data_ptr(), rs.data_ptr(), st)
+            Cc = torch.empty(M, strat.np, **f64)
+            Bs, bs = strat._slice_rows(strat.Rt, G)
+
+            def fn(it):
+                L.mcacq_ozaki_contract(_lib.TRI_UPPER, M, strat.np, strat.np, G, sl.data_ptr(), rs.data_ptr(), Bs.data_ptr(),
+                                       bs.data_ptr(), Cc.data_ptr(), strat.np, st)
+
+            ms = time_launch(fn, 2 * args.steps)
+            ach = alg_flops / (ms * 1e-3) * 1e-12
+            # roofline of THIS algorithm on the INT8 tensor pipe: every fp64 multiply-add costs G(G+1)/2 int8 multiply-adds;
+            # dense int8 peak of the part = 2 x the measured dense bf16 peak
+            peak_equiv = 2.0 * bf16_peak / pairs
+            return {"bound": "tensor", "kernel": "ozaki_imma_kernel (tcgen05 kind::i8, G=7 forward launch)", "achieved": ach,
+                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 10.37e9 * (M / 65536.0),
+                    "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
+                    "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
+                    "fp64_dgemm_peak_measured": fp64_peak_tf,
+                    "traffic_source": "ncu dram__bytes_read+write at M=65536 (profiles/r01_ozaki_int8.md)"}
+
+        roof = {"int8": int8_roofline, "dmma": dmma_roofline}
+        roofline = roof[args.contraction]()
+        roofline_alt = roof[other]()
+        roofline["step_alg_tflops"] = (2.0 * spec.q * spec.n * spec.n * b_total / world) / (ms_total / args.steps * 1e-3) * 1e-12
         if world == 1:
             sample_b = args.cpu_sample or (64 if spec.n >= 4096 else 256)
             val, sec, threads, sample = cpu_reference(args, data, spec, 1, 1, sample_b)
@@ -261,10 +315,16 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "chunk_q_batches": chunk, "per_gpu_q_batches": b_local,
                            "l2": "inputs larger than L2 (per-chunk working set %.1f GB)" % (2 * chunk * spec.q * model.prediction_strategy().np * 8 / 1e9),
-                           "parallelism": f"shard b over {world} GPU(s), all-gather of values"},
+                           "parallelism": f"shard b over {world} GPU(s), all-gather of values",
+                           "contraction": ("int8: Ozaki split of the fp64 contraction onto the INT8 tensor cores (tcgen05), "
+                                           "7/6 diagonals, parity-tested at 1e-9" if args.contraction == "int8"
+                                           else "dmma: FP64 DMMA tensor-core kernel")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
                         "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline}
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
+                "alt_mode": {"contraction": other, "value": pts_per_step * args.steps / (alt["ms_total"] * 1e-3),
+                             "ms_per_step": alt["ms_total"] / args.steps,
+                             "e2e_value": pts_per_step * args.steps / (alt["ms_e2e"] * 1e-3), "roofline": roofline_alt}}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
