@@ -275,7 +275,7 @@ def main():
                     "traffic_source": "ncu dram__bytes_read+write at M=16384 scaled to this M (profiles/README.md)"}
 
         def int8_roofline():
-            G = 7
+            G = 6
             pairs = G * (G + 1) // 2
             A = torch.rand(M, strat.np, **f64)
             sl = torch.empty(G, M, strat.np, dtype=torch.int8, device=dev)
@@ -293,12 +293,12 @@ def main():
             # roofline of THIS algorithm on the INT8 tensor pipe: every fp64 multiply-add costs G(G+1)/2 int8 multiply-adds;
             # dense int8 peak of the part = 2 x the measured dense bf16 peak
             peak_equiv = 2.0 * bf16_peak / pairs
-            return {"bound": "tensor", "kernel": "ozaki_imma_kernel (tcgen05 kind::i8, G=7 forward launch)", "achieved": ach,
-                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 10.37e9 * (M / 65536.0),
+            return {"bound": "tensor", "kernel": "ozaki_imma_kernel (tcgen05 kind::i8, G=6 forward launch)", "achieved": ach,
+                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": None,
                     "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
                     "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
                     "fp64_dgemm_peak_measured": fp64_peak_tf,
-                    "traffic_source": "ncu dram__bytes_read+write at M=65536 (profiles/r01_ozaki_int8.md)"}
+                    "traffic_source": "see profiles/r01_ozaki_int8.md (10.4 GB per launch measured for the 7-slice version)"}
 
         roof = {"int8": int8_roofline, "dmma": dmma_roofline}
         roofline = roof[args.contraction]()
@@ -317,7 +317,7 @@ def main():
                            "l2": "inputs larger than L2 (per-chunk working set %.1f GB)" % (2 * chunk * spec.q * model.prediction_strategy().np * 8 / 1e9),
                            "parallelism": f"shard b over {world} GPU(s), all-gather of values",
                            "contraction": ("int8: Ozaki split of the fp64 contraction onto the INT8 tensor cores (tcgen05), "
-                                           "7/6 diagonals, parity-tested at 1e-9" if args.contraction == "int8"
+                                           "6/5 diagonals of signed 8-bit slices, parity-tested at 1e-9" if args.contraction == "int8"
                                            else "dmma: FP64 DMMA tensor-core kernel")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
                         "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},

@@ -64,9 +64,9 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int i
   w.gSxb = (double*)take((size_t)M * (r > 0 ? r : 1) * 8);
   w.row_scale = (double*)take((size_t)M * 8);
   w.dU = (double*)take((size_t)M * d * 8);
-  // operands of the optional INT8 contraction: 7 slices of the M x np left operand + its row scales
+  // operands of the optional INT8 contraction: 6 slices of the M x np left operand + its row scales
   w.slice_scale = (double*)take((size_t)M * 8);
-  w.slices = (int8_t*)take(int8_mode ? (size_t)7 * M * np : 256);
+  w.slices = (int8_t*)take(int8_mode ? (size_t)6 * M * np : 256);
   w.bytes = off;
   return w;
 }
@@ -80,7 +80,7 @@ static int check_model(const mcacq_model* m) {
   if (m->contraction != 0 && m->contraction != 1) return MCACQ_EINVAL;
   if (m->contraction == 1) {
     if (!m->Rt_slices || !m->Rt_scale || !m->R_slices || !m->R_scale) return MCACQ_EINVAL;
-    if (m->g_fwd < 1 || m->g_fwd > 7 || m->g_bwd < 1 || m->g_bwd > 7) return MCACQ_EINVAL;
+    if (m->g_fwd < 1 || m->g_fwd > 6 || m->g_bwd < 1 || m->g_bwd > 6) return MCACQ_EINVAL;
   }
   return 0;
 }
@@ -94,7 +94,7 @@ static int run_posterior_stage(const mcacq_model* m, const mcacq_baseline* base,
   if ((rc = mcacq_scale_inputs(X, M, m->d, m->x_offset, m->x_coef, m->lengthscale, w.U, st))) return rc;
   if ((rc = mcacq_cov_cross(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, w.Kt, m->np, st))) return rc;
   if (m->contraction == 1) {
-    // Kt in (0, outputscale]: one fixed exponent for all rows, 2^e > outputscale
+    // Kt in (0, outputscale]: one fixed exponent for all rows, 2^e > outputscale >= |Kt|
     int e = 0;
     frexp(m->outputscale, &e);
     if ((rc = mcacq_slice_rows(w.Kt, M, m->np, m->np, m->np, m->g_fwd, 1, e, w.slices, w.slice_scale, st))) return rc;

@@ -2,17 +2,18 @@
 //
 //   C[M x N] (fp64) = A[M x K] * B^T,   B given as rows [N x K] (K contiguous),   triangular-aware in K
 //
-// Ozaki-style error-free splitting: both operands are pre-split into 7-bit signed slices with a power-of-two row
-// scale,  A[i][k] = 2^ea[i] * sum_p A_p[i][k] 128^-(p+1),  B[j][k] = 2^fb[j] * sum_q B_q[j][k] 128^-(q+1)
-// (`slice_rows_kernel` below).  Every slice product A_p B_q^T is EXACT in int32 (K * 127^2 < 2^31), so
-//   C[i][j] = 2^(ea[i] + fb[j]) * sum_{g < G} 128^-(g+2) * S_g[i][j],     S_g = sum_{p+q=g} A_p B_q^T,
-// with truncation error 2^-7G relative to (row max) x (column max): G = 7 diagonals give ~1e-11 on the posterior
-// variance, G = 6 ~1e-9 (measured, tools/ozaki_proto.py).  This is the same contraction as dgemm_tri.cu
+// Ozaki-style error-free splitting: both operands are pre-split into signed 8-bit slices (balanced radix-256 digits)
+// with a power-of-two row scale,  A[i][k] = ea[i] * sum_p A_p[i][k] 256^-(p+1),  B[j][k] = fb[j] * sum_q B_q[j][k] 256^-(q+1)
+// (`slice_rows_kernel` below).  Every slice product A_p B_q^T is EXACT in int32 (G * K * 128^2 < 2^31), so
+//   C[i][j] = ea[i] * fb[j] * sum_{g < G} 256^-(g+2) * S_g[i][j],     S_g = sum_{p+q=g} A_p B_q^T,
+// with truncation error ~2^-(8G-2) relative to (row max) x (column max): G = 6 diagonals (46-bit operands) keep the
+// posterior variance within ~1e-10, G = 5 ~1e-8 (tools/ozaki_test.py; the first version used 7-bit truncated digits
+// and needed G = 7 / 6 for the same accuracy).  This is the same contraction as dgemm_tri.cu
 // (gpytorch's `test_train_covar @ covar_cache`), executed at INT8 tensor-core rate instead of the FP64 DMMA pipe.
 //
 // Kernel structure (one persistent CTA per SM, 6 warps):
 //   warp 0 / lane 0 : TMA producer.  Per 64-byte k-block it loads G A-tiles (128 rows x 64 B) and G B-tiles
-//                     (64 rows x 64 B), SWIZZLE_64B, into a ring of 12*G KB stages (2 stages at G = 7, 3 at G <= 6;
+//                     (64 rows x 64 B), SWIZZLE_64B, into a ring of 12*G KB stages (3 stages at G = 6;
 //                     32-byte k-blocks with a 5-deep ring measured 25% slower).
 //   warp 1 / lane 0 : MMA issuer.  All G diagonals S_g live in TMEM at once (G x 64 columns of int32, 448 of 512),
 //                     so one k-block of operands feeds G(G+1)/2 slice products: 2.7x more tensor work per byte
@@ -31,7 +32,7 @@ namespace mcacq {
 
 constexpr int OZ_BM = 128, OZ_BN = 64;  // BK (bytes = int8 elements) is a template parameter: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
 constexpr int OZ_MAX_STAGES = 4;                    // ring depth is chosen at run time: as many 12*G KB stages as fit
-constexpr int OZ_MAXG = 7;
+constexpr int OZ_MAXG = 6;
 constexpr int OZ_GROUP_M = 8;
 constexpr int OZ_THREADS = 192;
 
@@ -239,7 +240,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       if (tl.kb1 > tl.kb0) {
         oz_mbar_wait(&acc_full, (uint32_t)(tile_i & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        double w = 1.0 / 16384.0;  // 128^-2
+        double w = 1.0 / 65536.0;  // 256^-2
         for (int g = 0; g < G; g++) {
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN);
 #pragma unroll
@@ -255,7 +256,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j++) acc[c + j] = fma(w, (double)(int32_t)v[j], acc[c + j]);
           }
-          w *= (1.0 / 128.0);
+          w *= (1.0 / 256.0);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -287,7 +288,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
 // ---- slicing ------------------------------------------------------------------------------------------------------
 // X[rows x K] (fp64, pitch ldx) -> G int8 slices [G][rows][Kp] (Kp = slice pitch >= K, zero padded) and the row scale
-// 2^e with |x| 2^-e < 1.  fixed_exp != INT_MIN: use that exponent for every row (K(X, X_train) <= outputscale).
+// 2^(e+2) with |x| < 2^e.  fixed_exp != INT_MIN: use that exponent for every row (K(X, X_train) <= outputscale).
 __global__ void __launch_bounds__(256)
 slice_rows_kernel(const double* __restrict__ X, int64_t rows, int K, int64_t ldx, int Kp, int G, int fixed_exp,
                   int8_t* __restrict__ S, double* __restrict__ scale) {
@@ -316,16 +317,21 @@ slice_rows_kernel(const double* __restrict__ X, int64_t rows, int K, int64_t ldx
     __syncthreads();
     e = s_exp;
   }
-  if (threadIdx.x == 0) scale[row] = ldexp(1.0, e);
+  // x = 2^(e+2) * sum_p D_p 256^-(p+1) with balanced digits D_p in [-128, 127]: round x to a (8G-2)-bit fixed-point
+  // integer relative to 2^e and peel signed bytes from the least significant end (carry-propagating, exact).  The
+  // extra headroom bit keeps the carries inside G bytes: G balanced bytes only reach 0.498 * 256^G.
+  if (threadIdx.x == 0) scale[row] = ldexp(1.0, e + 2);
   const size_t slice_stride = (size_t)rows * Kp;
   int8_t* out = S + row * (size_t)Kp;
+  const int shift = 8 * G - 2 - e;
   for (int k = threadIdx.x; k < Kp; k += 256) {
-    double r = (k < K) ? ldexp(x[k], -e) : 0.0;
-    for (int p = 0; p < G; p++) {
-      r *= 128.0;
-      const double qv = trunc(r);
-      out[p * slice_stride + k] = (int8_t)(int)qv;
-      r -= qv;
+    long long X = (k < K) ? __double2ll_rn(ldexp(x[k], shift)) : 0ll;
+    const long long lim = (1ll << (8 * G - 2));       // |x| < 2^e  =>  |X| <= 2^(8G-2)
+    X = X > lim ? lim : (X < -lim ? -lim : X);
+    for (int p = G - 1; p >= 0; p--) {
+      const int8_t dgt = (int8_t)(X & 0xFF);
+      out[p * slice_stride + k] = dgt;
+      X = (X - (long long)dgt) >> 8;
     }
   }
 }
@@ -434,7 +440,7 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   using namespace mcacq;
   if (!A_slices || !B_slices || !row_scale || !col_scale || !C || M < 0 || N <= 0 || K <= 0 || ldc < N) return MCACQ_EINVAL;
   if (G <= 0 || G > OZ_MAXG || (K % 16) != 0 || tri_mode < 0 || tri_mode > 2) return MCACQ_EINVAL;
-  if ((int64_t)K * 127 * 127 * G >= (int64_t)1 << 31) return MCACQ_ELIMIT;  // exact int32 accumulation of a diagonal
+  if ((int64_t)K * 128 * 128 * G >= (int64_t)1 << 31) return MCACQ_ELIMIT;  // exact int32 accumulation of a diagonal
   if (M == 0) return 0;
   // 128-byte k-blocks (full L2 lines, SWIZZLE_128B) when at least two stages of them fit, else 64-byte k-blocks
   const size_t smem_budget = 232448 - 2048 - 1024;  // 227 KB per CTA minus static shared memory and alignment slack

@@ -104,7 +104,7 @@ class DevicePredictionStrategy:
         self.Rt[:n, :n] = Linv
         del Linv
         self.train_chol = chol
-        # optional INT8 tensor-core contraction: 7-bit row-scaled slices of R^T (forward) and R (backward)
+        # optional INT8 tensor-core contraction: signed 8-bit row-scaled slices of R^T (forward) and R (backward)
         self.contraction = contraction
         if contraction not in ("dmma", "int8"):
             raise ValueError("contraction must be 'dmma' or 'int8'")
@@ -117,12 +117,12 @@ class DevicePredictionStrategy:
             y_mean=self.y_mean, y_std=self.y_std, x_offset=self.x_offset.data_ptr(), x_coef=self.x_coef.data_ptr(),
             lengthscale=self.lengthscale.data_ptr(), U_train=self.U_train.data_ptr(), alpha=self.alpha.data_ptr(),
             R=self.R.data_ptr(), Rt=self.Rt.data_ptr(),
-            contraction=1 if contraction == "int8" else 0, g_fwd=7, g_bwd=6, _pad=0,
+            contraction=1 if contraction == "int8" else 0, g_fwd=6, g_bwd=5, _pad=0,
             Rt_slices=_lib.ptr(self.Rt_slices), Rt_scale=_lib.ptr(self.Rt_scale),
             R_slices=_lib.ptr(self.R_slices), R_scale=_lib.ptr(self.R_scale),
         )
 
-    def _slice_rows(self, Mx: Tensor, G: int = 7) -> tuple[Tensor, Tensor]:
+    def _slice_rows(self, Mx: Tensor, G: int = 6) -> tuple[Tensor, Tensor]:
         rows, K = Mx.shape
         S = torch.empty(G, rows, K, dtype=torch.int8, device=self.device)
         scale = torch.empty(rows, dtype=torch.float64, device=self.device)

@@ -4,7 +4,7 @@
 is executed:
   * "dmma" -- hand-written FP64 tensor-core kernel (`csrc/dgemm_tri.cu`, DMMA.8x8x4);
   * "int8" -- Ozaki-style error-free split onto the INT8 tensor cores (`csrc/ozaki_imma.cu`, tcgen05 + TMEM + TMA),
-              7 diagonals forward / 6 backward: same 1e-9 value and 1e-7 gradient parity, ~2x faster.
+              6 diagonals of signed 8-bit slices forward / 5 backward: same 1e-9 value and 1e-7 gradient parity, ~2x faster.
 """
 from __future__ import annotations
 

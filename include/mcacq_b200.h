@@ -75,14 +75,14 @@ typedef struct {
   const double* R;           /* [np x np] covar_cache = L^{-T}, upper triangular, zero padded */
   const double* Rt;          /* [np x np] transpose of R (lower triangular), zero padded    */
   /* Optional INT8-tensor-core contraction (csrc/ozaki_imma.cu).  contraction = 0: FP64 DMMA (mcacq_dgemm_tri);
-   * contraction = 1: Ozaki split, g_fwd / g_bwd diagonals (7 / 6 keep 1e-9 on values / 1e-7 on gradients).      */
+   * contraction = 1: Ozaki split, g_fwd / g_bwd diagonals (6 / 5 keep 1e-9 on values / 1e-7 on gradients).      */
   int32_t contraction;
   int32_t g_fwd;
   int32_t g_bwd;
   int32_t _pad;
-  const int8_t* Rt_slices;   /* [7][np][np] row-scaled slices of R^T (row j = column j of R)  -- forward B operand */
+  const int8_t* Rt_slices;   /* [6][np][np] row-scaled slices of R^T (row j = column j of R)  -- forward B operand */
   const double* Rt_scale;    /* [np]                                                                             */
-  const int8_t* R_slices;    /* [7][np][np] row-scaled slices of R                            -- backward B operand */
+  const int8_t* R_slices;    /* [6][np][np] row-scaled slices of R                            -- backward B operand */
   const double* R_scale;     /* [np]                                                                             */
 } mcacq_model;
 
@@ -134,8 +134,8 @@ int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_
 
 /* ---- FP64-accurate contraction on the INT8 tensor cores (Ozaki-style splitting; csrc/ozaki_imma.cu) -------------
  * Optional replacement of mcacq_dgemm_tri for `test_train_covar @ covar_cache`:
- *   mcacq_slice_rows    : X[rows x K] (fp64) -> G signed 7-bit slices [G][rows][Kp] (int8) + row scale 2^e;
- *   mcacq_ozaki_contract: C[M x N] = 2^(ea+fb) * sum_{p+q<G} 128^-(p+q+2) A_p B_q^T  (tcgen05 kind::i8, exact int32
+ *   mcacq_slice_rows    : X[rows x K] (fp64) -> G signed 8-bit slices [G][rows][Kp] (balanced radix-256 digits) + row scale;
+ *   mcacq_ozaki_contract: C[M x N] = ea*fb * sum_{p+q<G} 256^-(p+q+2) A_p B_q^T  (tcgen05 kind::i8, exact int32
  *                         slice products, fp64 recombination); B slices are given as rows [N x K] (K contiguous).
  * tri_mode as in mcacq_dgemm_tri (which k-range of B^T is non-zero).                                              */
 int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, int G, int use_fixed_exp, int fixed_exp,
