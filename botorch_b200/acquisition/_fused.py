@@ -27,11 +27,13 @@ class BaselineOperands:
     A_base: Tensor  # r x np
     L_base: Tensor  # r x r
     desc: _lib.Baseline = None
+    A_base_absmax: Tensor = None
 
     def __post_init__(self):
         r = self.U_base.shape[0]
+        self.A_base_absmax = self.A_base.abs().amax(dim=1).contiguous()
         self.desc = _lib.Baseline(r=r, _pad=0, U_base=self.U_base.data_ptr(), A_base=self.A_base.data_ptr(),
-                                  L_base=self.L_base.data_ptr())
+                                  L_base=self.L_base.data_ptr(), A_base_absmax=self.A_base_absmax.data_ptr())
 
     @property
     def r(self) -> int:

@@ -19,6 +19,7 @@ namespace mcacq {
 
 // defined in blocks.cu / sample_reduce.cu / cov.cu
 int unscale_grad(const double* dU, int64_t rows, int d, const double* coef, const double* ls, double* dX, cudaStream_t st);
+int fill_value(double* p, int64_t n, double v, cudaStream_t st);
 
 }  // namespace mcacq
 
@@ -32,7 +33,8 @@ int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 
 struct Workspace {
-  double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale;
+  double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale, *mean_part,
+      *A_absmax;
   int8_t* slices;
   int32_t* counter;
   size_t bytes;
@@ -66,6 +68,8 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int i
   w.dU = (double*)take((size_t)M * d * 8);
   // operands of the optional INT8 contraction: 6 slices of the M x np left operand + its row scales
   w.slice_scale = (double*)take((size_t)M * 8);
+  w.A_absmax = (double*)take((size_t)M * 8);
+  w.mean_part = (double*)take(int8_mode ? (size_t)((np + 63) / 64) * M * 8 : 256);
   w.slices = (int8_t*)take(int8_mode ? (size_t)6 * M * np : 256);
   w.bytes = off;
   return w;
@@ -92,23 +96,31 @@ static int run_posterior_stage(const mcacq_model* m, const mcacq_baseline* base,
   const int r = base ? base->r : 0;
   int rc;
   if ((rc = mcacq_scale_inputs(X, M, m->d, m->x_offset, m->x_coef, m->lengthscale, w.U, st))) return rc;
-  if ((rc = mcacq_cov_cross(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, w.Kt, m->np, st))) return rc;
-  if (m->contraction == 1) {
-    // Kt in (0, outputscale]: one fixed exponent for all rows, 2^e > outputscale >= |Kt|
+  const bool int8 = (m->contraction == 1);
+  if (int8) {
+    // Kt in (0, outputscale]: one fixed exponent for all rows, 2^e > outputscale >= |Kt|.  The covariance kernel emits
+    // the slices and the partial means directly; the fp64 Kt never exists in this mode.
     int e = 0;
     frexp(m->outputscale, &e);
-    if ((rc = mcacq_slice_rows(w.Kt, M, m->np, m->np, m->np, m->g_fwd, 1, e, w.slices, w.slice_scale, st))) return rc;
+    if ((rc = mcacq_cov_cross_sliced(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, m->np, m->alpha,
+                                     m->g_fwd, e, w.slices, w.mean_part, st)))
+      return rc;
+    // row scale of the fixed-exponent slices: 2^(e+2) for every row
+    if ((rc = fill_value(w.slice_scale, M, ldexp(1.0, e + 2), st))) return rc;
     if ((rc = mcacq_ozaki_contract(MCACQ_TRI_UPPER, M, m->np, m->np, m->g_fwd, w.slices, w.slice_scale, m->Rt_slices,
                                    m->Rt_scale, w.A, m->np, st)))
       return rc;
   } else {
+    if ((rc = mcacq_cov_cross(m->kernel_id, m->outputscale, w.U, M, m->U_train, m->n, m->d, w.Kt, m->np, st))) return rc;
     if ((rc = mcacq_dgemm_tri(MCACQ_TRI_UPPER, M, m->np, w.Kt, m->R, w.A, w.counter, st))) return rc;
   }
   BlocksParams bp;
   bp.b = b; bp.q = q; bp.d = m->d; bp.np = m->np; bp.r = r;
   bp.kernel_id = m->kernel_id; bp.outputscale = m->outputscale; bp.mean_const = m->mean_const;
   bp.y_mean = m->y_mean; bp.y_std = m->y_std;
-  bp.A = w.A; bp.Kt = w.Kt; bp.alpha = m->alpha; bp.U = w.U;
+  bp.A = w.A; bp.Kt = int8 ? nullptr : w.Kt; bp.alpha = m->alpha; bp.U = w.U;
+  bp.mean_part = int8 ? w.mean_part : nullptr; bp.n_parts = ((m->np + 63) / 64 + 7) / 8;  // CT_PER_CTA = 8 column tiles per partial (cov.cu)
+  bp.A_absmax = w.A_absmax;
   bp.A_base = r > 0 ? base->A_base : nullptr;
   bp.U_base = r > 0 ? base->U_base : nullptr;
   bp.mean = w.mean; bp.Sxx = w.Sxx; bp.Sxb = w.Sxb;
@@ -167,9 +179,15 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   bp.U_base = r > 0 ? base->U_base : nullptr;
   bp.gmean = gmean; bp.gSxx = gSxx; bp.gSxb = gSxb;
   bp.row_scale = w.row_scale; bp.dU = w.dU;
+  // int8 mode: the kernel emits the slices of dA (scaled by a per-row bound) instead of the fp64 matrix
+  const bool fuse_slices = (model->contraction == 1) && (r == 0 || base->A_base_absmax != nullptr);
+  bp.emit_slices = fuse_slices ? 1 : 0; bp.G = model->g_bwd;
+  bp.slices = w.slices; bp.slice_scale = w.slice_scale; bp.A_absmax = w.A_absmax;
+  bp.Ab_absmax = r > 0 ? base->A_base_absmax : nullptr;
   if ((rc = posterior_blocks_bwd(bp, st))) return rc;
   if (model->contraction == 1) {
-    if ((rc = mcacq_slice_rows(w.A, M, model->np, model->np, model->np, model->g_bwd, 0, 0, w.slices, w.slice_scale, st)))
+    if (!fuse_slices &&
+        (rc = mcacq_slice_rows(w.A, M, model->np, model->np, model->np, model->g_bwd, 0, 0, w.slices, w.slice_scale, st)))
       return rc;
     if ((rc = mcacq_ozaki_contract(MCACQ_TRI_LOWER, M, model->np, model->np, model->g_bwd, w.slices, w.slice_scale,
                                    model->R_slices, model->R_scale, w.Kt, model->np, st)))

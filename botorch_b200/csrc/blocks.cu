@@ -47,11 +47,13 @@ posterior_blocks_kernel(BlocksParams p) {
   double accG[NB][QT][QT][2];
   double accB[NB][QT][RT > 0 ? RT : 1][2];
   double macc[NB][QT];
+  double amax[NB][QT];
 #pragma unroll
   for (int nb = 0; nb < NB; nb++)
 #pragma unroll
     for (int mi = 0; mi < QT; mi++) {
       macc[nb][mi] = 0.0;
+      amax[nb][mi] = 0.0;
 #pragma unroll
       for (int nj = 0; nj < QT; nj++) { accG[nb][mi][nj][0] = 0.0; accG[nb][mi][nj][1] = 0.0; }
 #pragma unroll
@@ -79,10 +81,14 @@ posterior_blocks_kernel(BlocksParams p) {
         bool ok = bok && i < q;
         int64_t row = bb * q + i;
         load4(p.A + row * np + kc, ok, af[mi]);
-        double kf[4];
-        load4(p.Kt + row * np + kc, ok, kf);
+        if (p.Kt != nullptr) {
+          double kf[4];
+          load4(p.Kt + row * np + kc, ok, kf);
 #pragma unroll
-        for (int s = 0; s < 4; s++) macc[nb][mi] = fma(kf[s], al[s], macc[nb][mi]);
+          for (int s = 0; s < 4; s++) macc[nb][mi] = fma(kf[s], al[s], macc[nb][mi]);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) amax[nb][mi] = fmax(amax[nb][mi], fabs(af[mi][s]));
       }
 #pragma unroll
       for (int s = 0; s < 4; s++)
@@ -108,8 +114,19 @@ posterior_blocks_kernel(BlocksParams p) {
       double mv = macc[nb][mi];
       mv += __shfl_xor_sync(0xffffffffu, mv, 1);
       mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+      double av = amax[nb][mi];
+      av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 1));
+      av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 2));
       const int i = mi * 8 + g;
-      if (t4 == 0 && i < q) p.mean[bb * q + i] = p.y_mean + p.y_std * (p.mean_const + mv);
+      if (t4 == 0 && i < q) {
+        if (p.mean_part != nullptr) {  // int8 mode: Kt * alpha was reduced per 64-column tile by the covariance kernel
+          const int64_t Mrows = p.b * q;
+          mv = 0.0;
+          for (int t = 0; t < p.n_parts; t++) mv += p.mean_part[(int64_t)t * Mrows + bb * q + i];
+        }
+        p.mean[bb * q + i] = p.y_mean + p.y_std * (p.mean_const + mv);
+        if (p.A_absmax != nullptr) p.A_absmax[bb * q + i] = av;
+      }
       if (i >= q) continue;
 #pragma unroll
       for (int nj = 0; nj <= mi; nj++)
@@ -178,6 +195,32 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
     }
   }
 
+  // int8 mode: exponent of an upper bound of |dA[i][:]| <= sum_j |C[i][j]| max|A[j][:]| + sum_j' |Cb[i][j']| max|A_base[j'][:]|
+  int shift[QT];
+  if (p.emit_slices) {
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      double bnd = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 2 * QT; kk++) {
+        const int j = kk * 4 + t4;
+        if (j < q) bnd = fma(fabs(cq[mi][kk]), p.A_absmax[bb * q + j], bnd);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2 * RT; kk++) {
+        const int j = kk * 4 + t4;
+        if (j < r) bnd = fma(fabs(cb[mi][kk]), p.Ab_absmax[j], bnd);
+      }
+      bnd += __shfl_xor_sync(0xffffffffu, bnd, 1);
+      bnd += __shfl_xor_sync(0xffffffffu, bnd, 2);
+      int ex = 0;
+      if (bnd > 0.0 && isfinite(bnd)) frexp(bnd * (1.0 + 1e-9), &ex);
+      shift[mi] = 8 * p.G - 2 - ex;
+      const int i = mi * 8 + g;
+      if (t4 == 0 && i < q) p.slice_scale[bb * q + i] = ldexp(1.0, ex + 2);
+    }
+  }
+  const size_t slice_stride = (size_t)p.b * q * np;
   double* Ab = p.A + bb * q * np;
 #pragma unroll 2
   for (int c0 = 0; c0 < np; c0 += 16) {
@@ -214,9 +257,18 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
     for (int mi = 0; mi < QT; mi++) {
       const int i = mi * 8 + g;
       if (i < q) {
-        double* dst = Ab + (int64_t)i * np + c0 + 4 * t4;
-        *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][0][0], acc[mi][1][0]);
-        *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[mi][0][1], acc[mi][1][1]);
+        if (p.emit_slices) {
+          const unsigned long long Y[4] = {balanced_bytes(__double2ll_rn(ldexp(acc[mi][0][0], shift[mi]))),
+                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][1][0], shift[mi]))),
+                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][0][1], shift[mi]))),
+                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][1][1], shift[mi])))};
+          int8_t* sdst = p.slices + ((size_t)(bb * q + i)) * np + c0 + 4 * t4;
+          for (int pp = 0; pp < p.G; pp++) *reinterpret_cast<unsigned*>(sdst + pp * slice_stride) = pack_digit4(Y, p.G - 1 - pp);
+        } else {
+          double* dst = Ab + (int64_t)i * np + c0 + 4 * t4;
+          *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][0][0], acc[mi][1][0]);
+          *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[mi][0][1], acc[mi][1][1]);
+        }
       }
     }
   }

@@ -35,66 +35,112 @@ __global__ void unscale_grad_kernel(const double* __restrict__ dU, int64_t total
 // Shared memory: U1^T tile [d][64], U2^T tile [d][64]  (dimension-major, so a thread's 4 points are
 // one 32-byte vector and a half-warp reads 512 contiguous bytes).
 constexpr int CT = 64;
+constexpr int CT_PER_CTA = 8;  // column tiles swept by one CTA in the slice-emitting variant
 
+// SLICES = true (int8 contraction mode): instead of the fp64 matrix the kernel emits the G signed 8-bit slices of
+// every entry (fixed exponent: 0 < k <= outputscale < 2^e; same digits as slice_rows_kernel in ozaki_imma.cu) and the
+// per-tile partial sums of K * alpha, so neither the fp64 K nor a separate slicing pass touches HBM.
+template <bool SLICES>
 __global__ void __launch_bounds__(256)
 cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U1, int64_t m1,
-                 const double* __restrict__ U2, int m2, int d, double* __restrict__ K, int64_t ldk) {
+                 const double* __restrict__ U2, int m2, int d, double* __restrict__ K, int64_t ldk,
+                 int8_t* __restrict__ S, int G, int fixed_exp, const double* __restrict__ alpha,
+                 double* __restrict__ mean_part, int64_t m1_total, int64_t row_base) {
   extern __shared__ __align__(16) double sm[];
   double* s1 = sm;             // [d][CT]
   double* s2 = sm + d * CT;    // [d][CT]
   const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.y * CT;
-  const int col0 = blockIdx.x * CT;
+  const int tx = tid & 15, ty = tid >> 4;
+  // SLICES: one CTA sweeps CT_PER_CTA consecutive column tiles so that the K * alpha partial sums need only
+  // ceil(tiles / CT_PER_CTA) slots per row; otherwise one tile per CTA.
+  const int tiles_per_cta = SLICES ? CT_PER_CTA : 1;
+  const int n_col_tiles = (int)((ldk + CT - 1) / CT);
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = (t_begin + tiles_per_cta < n_col_tiles) ? t_begin + tiles_per_cta : n_col_tiles;
 
   for (int idx = tid; idx < CT * d; idx += 256) {
     int p = idx / d, k = idx - p * d;  // coalesced read of point-major global rows
     int64_t gr = row0 + p;
     s1[k * CT + p] = (gr < m1) ? U1[gr * d + k] : 0.0;
-    int gc = col0 + p;
-    s2[k * CT + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
   }
-  __syncthreads();
+  double pm[4] = {0.0, 0.0, 0.0, 0.0};
 
-  const int tx = tid & 15, ty = tid >> 4;
-  double sq[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) sq[i][j] = 0.0;
+  for (int ct = t_begin; ct < t_end; ct++) {
+    const int col0 = ct * CT;
+    __syncthreads();  // previous tile's reads of s2 are done (and s1 is staged on the first pass)
+    for (int idx = tid; idx < CT * d; idx += 256) {
+      int p = idx / d, k = idx - p * d;
+      int gc = col0 + p;
+      s2[k * CT + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
+    }
+    __syncthreads();
 
-  for (int k = 0; k < d; k++) {
-    const double4 a4 = *reinterpret_cast<const double4*>(s1 + k * CT + ty * 4);
-    const double4 b4 = *reinterpret_cast<const double4*>(s2 + k * CT + tx * 4);
-    const double a[4] = {a4.x, a4.y, a4.z, a4.w};
-    const double bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    double sq[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        double df = a[i] - bb[j];
-        sq[i][j] = fma(df, df, sq[i][j]);
-      }
-  }
+      for (int j = 0; j < 4; j++) sq[i][j] = 0.0;
+
+    for (int k = 0; k < d; k++) {
+      const double4 a4 = *reinterpret_cast<const double4*>(s1 + k * CT + ty * 4);
+      const double4 b4 = *reinterpret_cast<const double4*>(s2 + k * CT + tx * 4);
+      const double a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const double bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double df = a[i] - bb[j];
+          sq[i][j] = fma(df, df, sq[i][j]);
+        }
+    }
 
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    int64_t gr = row0 + ty * 4 + i;
-    if (gr >= m1) continue;
-    double v[4];
+    for (int i = 0; i < 4; i++) {
+      int64_t gr = row0 + ty * 4 + i;
+      const bool row_ok = gr < m1;
+      if (!row_ok) continue;
+      double v[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int gc = col0 + tx * 4 + j;
-      v[j] = (gc < m2) ? kernel_value(kernel_id, outputscale, sq[i][j]) : 0.0;
+      for (int j = 0; j < 4; j++) {
+        int gc = col0 + tx * 4 + j;
+        v[j] = (gc < m2) ? kernel_value(kernel_id, outputscale, sq[i][j]) : 0.0;
+      }
+      int gc0 = col0 + tx * 4;
+      if (SLICES) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) pm[i] = fma(v[j], (gc0 + j < m2) ? alpha[gc0 + j] : 0.0, pm[i]);
+        if (gc0 < ldk) {  // ldk is a multiple of 16, so the 4 columns are all inside the pitch
+          const int shift = 8 * G - 2 - fixed_exp;
+          unsigned long long Y[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) Y[j] = balanced_bytes(__double2ll_rn(ldexp(v[j], shift)));
+          for (int pp = 0; pp < G; pp++)  // slice pp = digit G-1-pp (most significant first)
+            *reinterpret_cast<unsigned*>(S + ((size_t)pp * m1_total + row_base + gr) * ldk + gc0) = pack_digit4(Y, G - 1 - pp);
+        }
+        continue;
+      }
+      double* dst = K + gr * ldk + gc0;
+      if (gc0 + 3 < ldk && ((ldk & 1) == 0)) {
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (gc0 + j < ldk) dst[j] = v[j];
+      }
     }
-    int gc0 = col0 + tx * 4;
-    double* dst = K + gr * ldk + gc0;
-    if (gc0 + 3 < ldk && ((ldk & 1) == 0)) {
-      *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
-      *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
-    } else {
+  }
+  if (SLICES) {
+    // K * alpha over this CTA's columns: deterministic shuffle tree over the 16 lanes of a row, one writer per row
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (gc0 + j < ldk) dst[j] = v[j];
+    for (int i = 0; i < 4; i++) {
+      double v = pm[i];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int64_t gr = row0 + ty * 4 + i;
+      if (tx == 0 && gr < m1) mean_part[(int64_t)blockIdx.x * m1_total + row_base + gr] = v;
     }
   }
 }
@@ -253,6 +299,17 @@ extern "C" int mcacq_scale_inputs(const double* X, int64_t rows, int d, const do
 }
 
 namespace mcacq {
+__global__ void fill_value_kernel(double* p, int64_t n, double v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_value(double* p, int64_t n, double v, cudaStream_t st) {
+  if (n == 0) return 0;
+  fill_value_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
 int unscale_grad(const double* dU, int64_t rows, int d, const double* coef, const double* ls, double* dX,
                  cudaStream_t st) {
   int64_t total = rows * d;
@@ -266,19 +323,21 @@ int unscale_grad(const double* dU, int64_t rows, int d, const double* coef, cons
 }
 }  // namespace mcacq
 
-extern "C" int mcacq_cov_cross(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2,
-                               int m2, int d, double* K, int64_t ldk, void* stream) {
-  using namespace mcacq;
-  if (!U1 || !U2 || !K || m1 < 0 || m2 < 0 || d <= 0 || ldk < m2) return MCACQ_EINVAL;
+namespace mcacq {
+static int cov_cross_launch(bool sliced, int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2,
+                            int m2, int d, double* K, int64_t ldk, int8_t* S, int G, int fixed_exp, const double* alpha,
+                            double* mean_part, cudaStream_t st) {
   if (d > MCACQ_MAX_D) return MCACQ_ELIMIT;
   if (kernel_id != MCACQ_KERNEL_RBF && kernel_id != MCACQ_KERNEL_MATERN52) return MCACQ_EINVAL;
   if (m1 == 0 || ldk == 0) return 0;
   int64_t gy = (m1 + CT - 1) / CT;
   int gx = (int)((ldk + CT - 1) / CT);
+  if (sliced) gx = (gx + CT_PER_CTA - 1) / CT_PER_CTA;
   size_t smem = (size_t)2 * d * CT * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(cov_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MCACQ_MAX_D * CT * 8);
+    cudaFuncSetAttribute(cov_cross_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MCACQ_MAX_D * CT * 8);
+    cudaFuncSetAttribute(cov_cross_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MCACQ_MAX_D * CT * 8);
     attr = true;
   }
   // gridDim.y is limited to 65535: split very tall problems
@@ -287,12 +346,34 @@ extern "C" int mcacq_cov_cross(int kernel_id, double outputscale, const double* 
     int64_t ny = (gy - y0 < max_gy) ? gy - y0 : max_gy;
     int64_t r0 = y0 * CT;
     dim3 grid(gx, (unsigned)ny);
-    cov_cross_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(kernel_id, outputscale, U1 + r0 * d, m1 - r0, U2, m2, d,
-                                                                 K + r0 * ldk, ldk);
+    if (sliced)
+      cov_cross_kernel<true><<<grid, 256, smem, st>>>(kernel_id, outputscale, U1 + r0 * d, m1 - r0, U2, m2, d, nullptr, ldk,
+                                                      S, G, fixed_exp, alpha, mean_part, m1, r0);
+    else
+      cov_cross_kernel<false><<<grid, 256, smem, st>>>(kernel_id, outputscale, U1 + r0 * d, m1 - r0, U2, m2, d,
+                                                       K + r0 * ldk, ldk, nullptr, 0, 0, nullptr, nullptr, m1, r0);
     count_launch();
   }
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
+}
+}  // namespace mcacq
+
+extern "C" int mcacq_cov_cross(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2,
+                               int m2, int d, double* K, int64_t ldk, void* stream) {
+  if (!U1 || !U2 || !K || m1 < 0 || m2 < 0 || d <= 0 || ldk < m2) return MCACQ_EINVAL;
+  return mcacq::cov_cross_launch(false, kernel_id, outputscale, U1, m1, U2, m2, d, K, ldk, nullptr, 0, 0, nullptr, nullptr,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int mcacq_cov_cross_sliced(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2,
+                                      int m2, int d, int64_t ldk, const double* alpha, int G, int fixed_exp,
+                                      int8_t* slices, double* mean_part, void* stream) {
+  if (!U1 || !U2 || !alpha || !slices || !mean_part || m1 < 0 || m2 < 0 || d <= 0 || ldk < m2 || (ldk % 16) != 0)
+    return MCACQ_EINVAL;
+  if (G < 1 || G > 6) return MCACQ_EINVAL;
+  return mcacq::cov_cross_launch(true, kernel_id, outputscale, U1, m1, U2, m2, d, nullptr, ldk, slices, G, fixed_exp, alpha,
+                                 mean_part, (cudaStream_t)stream);
 }
 
 namespace mcacq {

@@ -8,7 +8,10 @@ struct BlocksParams {
   int kernel_id;
   double outputscale, mean_const, y_mean, y_std;
   const double* A;      // [b*q x np]
-  const double* Kt;     // [b*q x np]
+  const double* Kt;     // [b*q x np]   (nullptr in int8 mode: the mean comes from mean_part)
+  const double* mean_part;  // [n_parts x b*q] per-column-tile partial sums of Kt * alpha (int8 mode)
+  int n_parts;
+  double* A_absmax;     // [b*q] max_k |A[i][k]| (optional; feeds the exponent bound of the backward slices)
   const double* alpha;  // [np]
   const double* U;      // [b*q x d]
   const double* A_base; // [r x np]
@@ -32,6 +35,12 @@ struct BlocksBwdParams {
   const double* gSxb;     // [b x q x r]
   double* row_scale;      // [b*q]
   double* dU;             // [b*q x d]
+  // int8 contraction mode: emit the G signed 8-bit slices of dA directly (no fp64 dA), scaled by a per-row bound
+  int emit_slices, G;
+  int8_t* slices;             // [G][b*q][np]
+  double* slice_scale;        // [b*q]
+  const double* A_absmax;     // [b*q]  max_k |A[i][k]| from the forward pass
+  const double* Ab_absmax;    // [r]    max_k |A_base[j][k]|
 };
 
 struct SRParams {

@@ -93,6 +93,7 @@ typedef struct {
   const double* U_base;  /* [r x d] scaled baseline inputs                                  */
   const double* A_base;  /* [r x np] K(X_base, X_train) R                                   */
   const double* L_base;  /* [r x r] lower Cholesky of the (untransformed) posterior cov of f(X_base) */
+  const double* A_base_absmax; /* [r] max_k |A_base[j][k]| (optional; lets the int8 backward emit its slices fused) */
 } mcacq_baseline;
 
 /* Monte-Carlo operands.                                                                     */
@@ -115,6 +116,13 @@ int mcacq_scale_inputs(const double* X, int64_t rows, int d, const double* x_off
 /* K[i][j] = k(U1[i], U2[j]) for i < m1, j < m2; columns m2..ldk-1 of each row are zero-filled. */
 int mcacq_cov_cross(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
                     int d, double* K, int64_t ldk, void* stream);
+
+/* int8-contraction variant of mcacq_cov_cross: emits the G signed 8-bit slices [G][m1][ldk] of K (fixed exponent:
+ * 0 < k <= outputscale < 2^fixed_exp), the per-512-column partial sums mean_part[ceil(ldk/512)][m1] of K * alpha, and
+ * no fp64 matrix.  ldk must be a multiple of 16; columns m2..ldk-1 are zero.                                      */
+int mcacq_cov_cross_sliced(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
+                           int d, int64_t ldk, const double* alpha, int G, int fixed_exp, int8_t* slices,
+                           double* mean_part, void* stream);
 
 /* dU1[i][:] = sum_j W[i][j] * d k(U1[i], U2[j]) / d U1[i]   (+= if accumulate).             */
 int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,

@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
     from botorch_b200 import _lib
 
     assert ctypes.sizeof(_lib.Model) == 4 * 4 + 4 * 8 + 7 * 8 + 4 * 4 + 4 * 8
-    assert ctypes.sizeof(_lib.Baseline) == 8 + 3 * 8
+    assert ctypes.sizeof(_lib.Baseline) == 8 + 4 * 8
     assert ctypes.sizeof(_lib.MC) == 8 + 2 * 8 + 2 * 8
 
 
