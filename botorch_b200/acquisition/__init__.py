@@ -3,3 +3,5 @@ from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement  # noqa
 from .monte_carlo import MCAcquisitionFunction, SampleReducingMCAcquisitionFunction  # noqa: F401
 from .objective import (GenericMCObjective, IdentityMCObjective, LinearMCObjective, MCAcquisitionObjective,  # noqa: F401
                         PosteriorTransform)
+from .mc_improvement import (qExpectedImprovement, qNoisyExpectedImprovement, qProbabilityOfImprovement,  # noqa: F401
+                             qSimpleRegret)

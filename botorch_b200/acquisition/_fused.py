@@ -50,9 +50,11 @@ class MCOperands:
     tau_max: float
     fat: bool
     desc: _lib.MC = None
+    mode: int | None = None  # utility mode override (2 qEI/qNEI, 3 qSimpleRegret, 4 qPI); None -> int(fat)
 
     def __post_init__(self):
-        self.desc = _lib.MC(S=self.Zt.shape[1], fat=int(self.fat), tau_relu=float(self.tau_relu),
+        self.desc = _lib.MC(S=self.Zt.shape[1], fat=int(self.fat) if self.mode is None else int(self.mode),
+                            tau_relu=float(self.tau_relu),
                             tau_max=float(self.tau_max), Zt=self.Zt.data_ptr(), best=self.best.data_ptr())
 
 

@@ -61,6 +61,7 @@ class LogImprovementMCAcquisitionFunction(SampleReducingMCAcquisitionFunction):
                          constraints=constraints, eta=eta, fat=fat)
         self.tau_max = tau_max
         self._mc_cache: dict = {}
+        self._utility_mode: int | None = None  # set by the non-log subclasses (qEI / qNEI / qSR / qPI)
 
     # ---- fused-route plumbing -------------------------------------------------------------------
     def _fusable(self, X: Tensor) -> bool:
@@ -103,7 +104,8 @@ class qLogExpectedImprovement(LogImprovementMCAcquisitionFunction):
             if self.best_f.numel() != 1:
                 raise BotorchError("The fused qLogEI route expects a scalar `best_f`.")
             best = torch.full((S,), float(self.best_f), device=X.device, dtype=torch.float64)
-            ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat)
+            ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat,
+                             mode=self._utility_mode)
             self._mc_cache = {key: ops}
         return ops
 
@@ -236,7 +238,8 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
             S = self.sample_shape.numel()
             Zt = self.sampler.base_samples.reshape(S, r + q).t().contiguous()
             best = self._baseline_best_f.reshape(S).to(device=X.device, dtype=torch.float64).contiguous()
-            ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat)
+            ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat,
+                             mode=self._utility_mode)
             self._mc_cache = {key: ops}
         return ops
 

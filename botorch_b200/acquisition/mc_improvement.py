@@ -1,0 +1,88 @@
+"""Non-log sample-reducing MC acquisition functions on the same fused kernel:
+qExpectedImprovement (botorch/acquisition/monte_carlo.py:351-437), qNoisyExpectedImprovement (:440-673),
+qProbabilityOfImprovement (:676-763), qSimpleRegret (:766-830).  They differ from qLogEI / qLogNEI only in the
+per-sample utility and the reductions (`torch.amax` over q, `torch.mean` over the MC samples), which are template-free
+modes of `csrc/sample_reduce.cu`; everything upstream (covariance, contraction, posterior blocks, Cholesky, samples) is
+shared.  Anything the fused kernel does not cover falls back to the generic torch-op route."""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+from torch import Tensor
+
+from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement
+
+
+def _use_plain_reductions(acqf) -> None:
+    sample_dim = tuple(range(len(acqf.sample_shape)))
+    acqf._sample_reduction = partial(torch.mean, dim=sample_dim)
+    acqf._q_reduction = partial(torch.amax, dim=-1)
+
+
+class qExpectedImprovement(qLogExpectedImprovement):
+    """MC-based batch Expected Improvement: mean_S max_q relu(y - best_f)."""
+
+    _log = False
+
+    def __init__(self, model, best_f, sampler=None, objective=None, posterior_transform=None, X_pending=None,
+                 constraints=None, eta=1e-3) -> None:
+        super().__init__(model=model, best_f=best_f, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending, constraints=constraints, eta=eta)
+        _use_plain_reductions(self)
+        self._utility_mode = 2
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        return (obj - self.best_f.unsqueeze(-1).to(obj)).clamp_min(0)
+
+
+class qSimpleRegret(qLogExpectedImprovement):
+    """MC-based batch Simple Regret: mean_S max_q y."""
+
+    _log = False
+
+    def __init__(self, model, sampler=None, objective=None, posterior_transform=None, X_pending=None) -> None:
+        super().__init__(model=model, best_f=0.0, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending)
+        _use_plain_reductions(self)
+        self._utility_mode = 3
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        return obj
+
+
+class qProbabilityOfImprovement(qLogExpectedImprovement):
+    """MC-based batch Probability of Improvement: mean_S max_q sigmoid((y - best_f) / tau)."""
+
+    _log = False
+
+    def __init__(self, model, best_f, sampler=None, objective=None, posterior_transform=None, X_pending=None,
+                 tau: float = 1e-3, constraints=None, eta=1e-3) -> None:
+        super().__init__(model=model, best_f=best_f, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending, constraints=constraints, eta=eta,
+                         tau_relu=tau)
+        self.register_buffer("tau", torch.as_tensor(tau))
+        _use_plain_reductions(self)
+        self._utility_mode = 4
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        return torch.sigmoid((obj - self.best_f.unsqueeze(-1).to(obj)) / self.tau)
+
+
+class qNoisyExpectedImprovement(qLogNoisyExpectedImprovement):
+    """MC-based batch Noisy Expected Improvement: mean_S max_q relu(y - max_j y_baseline,j), cached-root sampling."""
+
+    _log = False
+
+    def __init__(self, model, X_baseline: Tensor, sampler=None, objective=None, posterior_transform=None, X_pending=None,
+                 prune_baseline: bool = True, cache_root: bool = True, constraints=None, eta=1e-3,
+                 marginalize_dim=None) -> None:
+        super().__init__(model=model, X_baseline=X_baseline, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending, constraints=constraints, eta=eta,
+                         prune_baseline=prune_baseline, cache_root=cache_root, marginalize_dim=marginalize_dim,
+                         incremental=False)
+        _use_plain_reductions(self)
+        self._utility_mode = 2
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        return (obj - self.compute_best_f(obj).unsqueeze(-1)).clamp_min(0)

@@ -79,3 +79,13 @@ class SampleReducingMCAcquisitionFunction(MCAcquisitionFunction):
         if self._constraints is not None:
             raise UnsupportedError("Outcome constraints are on the 'next' list of botorch_b200 (SURVEY.md section 8f N3).")
         return acqval
+
+
+def __getattr__(name: str):
+    """qExpectedImprovement & co. live in `mc_improvement` (they build on the fused classes of `logei`, which imports
+    this module); expose them under the reference's module path lazily."""
+    if name in ("qExpectedImprovement", "qNoisyExpectedImprovement", "qProbabilityOfImprovement", "qSimpleRegret"):
+        from . import mc_improvement
+
+        return getattr(mc_improvement, name)
+    raise AttributeError(name)

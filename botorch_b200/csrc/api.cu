@@ -218,6 +218,7 @@ extern "C" int mcacq_posterior_backward(const mcacq_model* model, const double* 
 static int check_mc(const mcacq_mc* mc) {
   if (!mc || !mc->Zt || !mc->best || mc->S <= 0) return MCACQ_EINVAL;
   if (!(mc->tau_relu > 0.0) || !(mc->tau_max > 0.0)) return MCACQ_EINVAL;
+  if (mc->fat < 0 || mc->fat > 4) return MCACQ_EINVAL;
   return 0;
 }
 

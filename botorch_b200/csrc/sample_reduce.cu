@@ -36,8 +36,27 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // log-improvement value and derivative w.r.t. z (the improvement y - best).
+// Utility modes (mcacq_mc.fat):  0 log_softplus + smooth_amax + logmeanexp   (qLogEI / qLogNEI, fat=False)
+//                                 1 log_fatplus  + fatmax      + logmeanexp   (qLogEI / qLogNEI, default)
+//                                 2 relu(z)      + amax        + mean         (qEI / qNEI,  monte_carlo.py:427-437, 607-616)
+//                                 3 y            + amax        + mean         (qSimpleRegret, :821-830; best = 0)
+//                                 4 sigmoid(z/tau_relu) + amax + mean         (qProbabilityOfImprovement, :752-763)
 template <bool GRAD>
 __device__ __forceinline__ double log_improve(double z, double tau, double inv_tau, int fat, double& dli) {
+  if (fat == 2) {
+    if (GRAD) dli = (z > 0.0) ? 1.0 : 0.0;
+    return fmax(z, 0.0);
+  }
+  if (fat == 3) {
+    if (GRAD) dli = 1.0;
+    return z;
+  }
+  if (fat == 4) {
+    const double u = z * inv_tau;
+    const double sg = (u >= 0.0) ? 1.0 / (1.0 + exp(-u)) : exp(u) / (1.0 + exp(u));
+    if (GRAD) dli = sg * (1.0 - sg) * inv_tau;
+    return sg;
+  }
   if (fat) {
     const double u = z * inv_tau;
     double sp, dsp;
@@ -80,6 +99,17 @@ __device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, doub
   double M = -CUDART_INF;
 #pragma unroll
   for (int i = 0; i < QMAX; i++) if (i < q) M = fmax(M, li[i]);
+  if (fat >= 2) {  // torch.amax over q: gradient split evenly among ties
+    if (GRAD) {
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) if (i < q) cnt += (li[i] == M) ? 1 : 0;
+      const double wgt = 1.0 / (double)(cnt > 0 ? cnt : 1);
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) if (i < q) w[i] = (li[i] == M) ? wgt : 0.0;
+    }
+    return M;
+  }
   if (isinf(M) || isnan(M)) {
     // _inf_max_helper: the result is the sum of the infinite maxima; gradient 1 on those entries
     double res = 0.0;
@@ -290,26 +320,32 @@ sample_reduce_fwd_kernel(SRParams p) {
           } else li[i] = -CUDART_INF;
         }
         const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
-        if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
+        if (p.fat >= 2) ls += fm;  // plain mean over the samples
+        else if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
         else lse_push(lm, ls, fm);
       }
     }
   }
   if (nonfinite) s_nonfinite = 1;
-  // ---- CTA logsumexp
+  // ---- CTA logsumexp (modes 0/1) or sum (modes >= 2), fixed combination order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double m2 = __shfl_xor_sync(0xffffffffu, lm, o);
     const double s2 = __shfl_xor_sync(0xffffffffu, ls, o);
-    lse_merge(lm, ls, m2, s2);
+    if (p.fat >= 2) ls += s2;
+    else lse_merge(lm, ls, m2, s2);
   }
   if (lane == 0) { red[2 * warp] = lm; red[2 * warp + 1] = ls; }
   __syncthreads();
   if (tid == 0) {
     double m = red[0], s = red[1];
-    for (int w = 1; w < SR_WARPS; w++) lse_merge(m, s, red[2 * w], red[2 * w + 1]);
+    for (int w = 1; w < SR_WARPS; w++) {
+      if (p.fat >= 2) s += red[2 * w + 1];
+      else lse_merge(m, s, red[2 * w], red[2 * w + 1]);
+    }
     double res;
-    if (S == 0 || m == -CUDART_INF) res = -CUDART_INF;
+    if (p.fat >= 2) res = s / (double)S;
+    else if (S == 0 || m == -CUDART_INF) res = -CUDART_INF;
     else if (isinf(m)) res = m;
     else res = m + log(s) - log((double)S);
     if (s_info & MCACQ_INFO_NOT_PSD) res = CUDART_NAN;
@@ -394,7 +430,8 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           }
           const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, inv_tau_max, p.fat, w);
           double ws;
-          if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
+          if (p.fat >= 2) ws = gout / (double)S;
+          else if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
           else ws = gout * exp(fm - lse_total);
           double* gys = gy + (size_t)(s0 + ns - c0) * GP;
 #pragma unroll

@@ -99,7 +99,9 @@ typedef struct {
 /* Monte-Carlo operands.                                                                     */
 typedef struct {
   int32_t S;           /* number of MC samples                                              */
-  int32_t fat;         /* 1: log_fatplus + fatmax, 0: log_softplus + smooth_amax            */
+  int32_t fat;         /* utility mode: 1 log_fatplus+fatmax+logmeanexp (qLogEI/qLogNEI), 0 log_softplus+smooth_amax+
+                        * logmeanexp, 2 relu+amax+mean (qEI/qNEI), 3 identity+amax+mean (qSimpleRegret),
+                        * 4 sigmoid((y-best)/tau_relu)+amax+mean (qProbabilityOfImprovement)  */
   double tau_relu;
   double tau_max;
   const double* Zt;    /* [(r + q) x S] base samples, TRANSPOSED (sample index contiguous)  */

@@ -118,3 +118,30 @@ def value_and_grad(acqf, X: Tensor):
     vals = acqf(Xg)
     (g,) = torch.autograd.grad(vals.sum(), Xg)
     return vals.detach(), g
+
+
+# ---- non-log sample-reducing utilities ------------------------------------------------------
+def oracle_qei(orc: OracleQLogEI, X: Tensor) -> Tensor:
+    """qExpectedImprovement (monte_carlo.py:427-437 + default amax / mean reductions :268-290)."""
+    obj = orc.samples(X if X.dim() > 2 else X.unsqueeze(0)).squeeze(-1)
+    return (obj - orc.best_f.to(obj)).clamp_min(0).amax(dim=-1).mean(dim=0)
+
+
+def oracle_qsr(orc: OracleQLogEI, X: Tensor) -> Tensor:
+    """qSimpleRegret (monte_carlo.py:821-830)."""
+    obj = orc.samples(X if X.dim() > 2 else X.unsqueeze(0)).squeeze(-1)
+    return obj.amax(dim=-1).mean(dim=0)
+
+
+def oracle_qpi(orc: OracleQLogEI, X: Tensor, tau: float = 1e-3) -> Tensor:
+    """qProbabilityOfImprovement (monte_carlo.py:752-763)."""
+    obj = orc.samples(X if X.dim() > 2 else X.unsqueeze(0)).squeeze(-1)
+    return torch.sigmoid((obj - orc.best_f.to(obj)) / tau).amax(dim=-1).mean(dim=0)
+
+
+def oracle_qnei(orc: OracleQLogNEI, X: Tensor) -> Tensor:
+    """qNoisyExpectedImprovement, cached-root path (monte_carlo.py:607-616)."""
+    X = X if X.dim() > 2 else X.unsqueeze(0)
+    obj = orc._f_X_samples(X).squeeze(-1)
+    best = orc.baseline_best_f.view(orc.S, *([1] * (obj.dim() - 1)))
+    return (obj - best).clamp_min(0).amax(dim=-1).mean(dim=0)
