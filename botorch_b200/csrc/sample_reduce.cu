@@ -187,7 +187,8 @@ sample_reduce_fwd_kernel(SRParams p) {
   const int QP = coef_pitch(q);
   double* coefT = sm;                          // [(r+q)][QP]
   double* brow = coefT + (size_t)(r + q) * QP; // [q][r]   row-major scratch for the triangular solve
-  double* Tm = brow + (size_t)q * r;           // [q][q]
+  double* Tm = brow + (size_t)q * (r > q ? r : q);  // [q][q]  (scratch is q*max(r,q): it later holds the q x q factor,
+                                                    //  which must not alias T or the jitter retries would re-read garbage)
   double* smean = Tm + q * q;                  // [q]
   double* red = smean + q;                     // [2 * SR_WARPS]
   __shared__ int s_info;
