@@ -30,7 +30,10 @@
 
 namespace mcacq {
 
-constexpr int OZ_BM = 128, OZ_BN = 64;  // BK (bytes = int8 elements) is a template parameter: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+constexpr int OZ_BM = 128;               // BK (bytes = int8 elements) is a template parameter: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+constexpr int OZ_MAX_BN = 256;           // the column-tile width BN is a template parameter: the widest multiple of 16 with G * BN <= 512
+                                         // TMEM columns (G = 6: 80, G = 5: 96, G = 4: 128), because the operand bytes an SM has to
+                                         // ingest per MAC fall as BM * BN / (BM + BN)
 constexpr int OZ_MAX_STAGES = 4;                    // ring depth is chosen at run time: as many 12*G KB stages as fit
 constexpr int OZ_MAXG = 6;
 constexpr int OZ_GROUP_M = 8;
@@ -93,7 +96,7 @@ struct OzTile { int64_t mt; int nt; int kb0, kb1; };
 // t-th CLUSTER tile in the static order (a cluster tile = CM x CN adjacent CTA tiles that share operand loads);
 // returns false past the end.  The k-range is the union over the cluster's column tiles (the extra k-blocks of the
 // narrower columns multiply stored zeros of the triangular factor).
-template <int OZ_BK, int CM, int CN>
+template <int OZ_BK, int OZ_BN, int CM, int CN>
 __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, OzTile& o) {
   const int64_t cm_tiles = (m_tiles + CM - 1) / CM;
   const int cn_tiles = (n_tiles + CN - 1) / CN;
@@ -113,7 +116,7 @@ __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles,
   return true;
 }
 
-template <int OZ_BK, int CM, int CN>
+template <int OZ_BK, int OZ_BN, int CM, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
                   int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
@@ -124,7 +127,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int stage_bytes = G * (OZ_A_TILE + OZ_B_TILE);
   __shared__ __align__(8) uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
-  __shared__ double s_col[OZ_BN];
+  __shared__ double s_col[OZ_MAX_BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
   const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
@@ -163,7 +166,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // ================= TMA producer =================
       int64_t it = 0;  // k-block counter across tiles
       OzTile tl;
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters) {
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters) {
         const int row0 = (int)((tl.mt * CM + rm) * OZ_BM), col0 = (tl.nt * CN + rn) * OZ_BN;
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
           const int s = (int)(it % stages);
@@ -188,7 +191,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       int64_t it = 0, tile_i = 0;
       OzTile tl;
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
         if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
           oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -209,7 +212,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               const int ncols = (G - p) * OZ_BN;
               for (int c0 = 0; c0 < ncols; c0 += 256) {
                 const int nn = (ncols - c0 < 256) ? (ncols - c0) : 256;
-                const uint64_t bd = oz_desc<OZ_BK>(st + G * OZ_A_TILE + (c0 / OZ_BN) * OZ_B_TILE) + 2 * k;
+                const uint64_t bd = oz_desc<OZ_BK>(st + G * OZ_A_TILE + c0 * OZ_BK) + 2 * k;  // stacked slices are contiguous rows
                 const uint32_t idesc_n = idesc_base | ((uint32_t)(nn >> 3) << 17);
                 oz_umma(tmem_base + (uint32_t)(p * OZ_BN + c0), ad, bd, idesc_n, (first && p == 0 && k == 0) ? 0u : 1u);
               }
@@ -228,55 +231,78 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int etid = tid - 64;                // 0..127
     int64_t tile_i = 0;
     OzTile tl;
-    for (int64_t t = cluster_id; oz_tile<OZ_BK, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
       const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
       const int col0 = (tl.nt * CN + rn) * OZ_BN;
       // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
-      if (etid < OZ_BN) s_col[etid] = (col0 + etid < N) ? col_scale[col0 + etid] : 0.0;
+      for (int c = etid; c < OZ_BN; c += 128) s_col[c] = (col0 + c < N) ? col_scale[col0 + c] : 0.0;
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      double acc[OZ_BN];
-#pragma unroll
-      for (int c = 0; c < OZ_BN; c++) acc[c] = 0.0;
-      if (tl.kb1 > tl.kb0) {
+      const bool have_acc = tl.kb1 > tl.kb0;
+      if (have_acc) {
         oz_mbar_wait(&acc_full, (uint32_t)(tile_i & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        double w = 1.0 / 65536.0;  // 256^-2
-        for (int g = 0; g < G; g++) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN);
+      }
+      const bool row_ok = row < M;
+      const double rs = row_ok ? row_scale[row] : 0.0;
+      double* dst = C + (row_ok ? row : 0) * ldc + col0;
+      const bool vec_ok = (ldc & 1) == 0;
+      // 16 output columns at a time: all G diagonals of the chunk are fetched from TMEM, combined in fp64 with the
+      // weights 256^-(g+2), scaled and stored (one 128-byte line per thread and chunk)
+#pragma unroll 1
+      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        double acc[16];
 #pragma unroll
-          for (int c = 0; c < OZ_BN; c += 32) {
-            uint32_t v[32];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                         : "r"(taddr + c));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; j++) acc[j] = 0.0;
+        if (have_acc) {
+          uint32_t v[OZ_MAXG][16];
 #pragma unroll
-            for (int j = 0; j < 32; j++) acc[c + j] = fma(w, (double)(int32_t)v[j], acc[c + j]);
+          for (int g = 0; g < OZ_MAXG; g++) {
+            if (g < G) {
+              const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN + c0);
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                           : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]), "=r"(v[g][6]),
+                             "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]), "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]),
+                             "=r"(v[g][13]), "=r"(v[g][14]), "=r"(v[g][15])
+                           : "r"(taddr));
+            }
           }
-          w *= (1.0 / 256.0);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) oz_mbar_arrive(&acc_empty);
-      } else {
-        // empty k-range (cannot happen for the triangular factors, kept for dense corner cases): still hand the
-        // accumulators back so the MMA thread's phase bookkeeping stays aligned
-        if (lane == 0) oz_mbar_arrive(&acc_empty);
-      }
-      if (row < M && col0 < N) {
-        const double rs = row_scale[row];
-        double* dst = C + row * ldc + col0;
-        if (col0 + OZ_BN <= N && (ldc & 1) == 0) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // Three neighbouring diagonals are merged exactly in int64 (|S_g| < 2^31, so the sum stays below 2^48) and
+          // converted with the 2^52 + 2^51 magic constant: one DADD + one DFMA per triple instead of an I2F.F64 (16/clk/SM)
+          // and a DFMA per diagonal.
+          double w = 1.0 / 4294967296.0;  // 256^-4: weight of the last member of the triple (S_0, S_1, S_2)
 #pragma unroll
-          for (int c = 0; c < OZ_BN; c += 2)
-            *reinterpret_cast<double2*>(dst + c) = make_double2(acc[c] * rs * s_col[c], acc[c + 1] * rs * s_col[c + 1]);
-        } else {
-          for (int c = 0; c < OZ_BN; c++) if (col0 + c < N) dst[c] = acc[c] * rs * s_col[c];
+          for (int g0 = 0; g0 < OZ_MAXG; g0 += 3) {
+            if (g0 < G) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                const long long s0 = (long long)(int32_t)v[g0][j];
+                const long long s1 = (g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1][j] : 0ll;
+                const long long s2 = (g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2][j] : 0ll;
+                const long long t = s0 * 65536ll + s1 * 256ll + s2;
+                const double d = __longlong_as_double(0x4338000000000000ll + t) - 6755399441055744.0;
+                acc[j] = fma(w, d, acc[j]);
+              }
+              w *= (1.0 / 16777216.0);
+            }
+          }
+        }
+        if (row_ok && col0 + c0 < N) {
+          if (col0 + c0 + 16 <= N && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2)
+              *reinterpret_cast<double2*>(dst + c0 + j) =
+                  make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+          } else {
+            for (int j = 0; j < 16; j++) if (col0 + c0 + j < N) dst[c0 + j] = acc[j] * rs * s_col[c0 + j];
+          }
         }
       }
+      // hand the accumulators back (also for an empty k-range, which cannot happen for the triangular factors, so
+      // that the MMA thread's phase bookkeeping stays aligned)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive(&acc_empty);
       asm volatile("bar.sync 1, 128;" ::: "memory");  // s_col reuse
     }
   }
@@ -366,11 +392,11 @@ static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_
   return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
 }
 
-template <int BKB, int CM, int CN>
+template <int BKB, int OZ_BN, int CM, int CN>
 static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M, int N, int K, int G,
                        int stages, size_t smem, size_t smem_budget, const double* row_scale, const double* col_scale,
                        double* C, int64_t ldc, cudaStream_t st) {
-  auto kern = ozaki_imma_kernel<BKB, CM, CN>;
+  auto kern = ozaki_imma_kernel<BKB, OZ_BN, CM, CN>;
   static int max_clusters = -1;
   constexpr int CS = CM * CN;
   cudaLaunchConfig_t cfg = {};
@@ -410,15 +436,24 @@ static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri
   return 0;
 }
 
-static int oz_launch(int bk, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M,
+static int oz_launch(int bk, int bn, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M,
                      int N, int K, int G, int stages, size_t smem, size_t smem_budget, const double* row_scale,
                      const double* col_scale, double* C, int64_t ldc, cudaStream_t st) {
-#define OZ_CASE(B, A_, C_) if (bk == B && cm == A_ && cn == C_) \
-    return oz_launch_t<B, A_, C_>(mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc, st);
-  OZ_CASE(64, 1, 1) OZ_CASE(64, 2, 2) OZ_CASE(64, 1, 4) OZ_CASE(64, 2, 4) OZ_CASE(64, 2, 1) OZ_CASE(64, 1, 2) OZ_CASE(64, 4, 2)
-  OZ_CASE(128, 1, 1) OZ_CASE(128, 2, 2) OZ_CASE(128, 1, 4) OZ_CASE(128, 2, 4)
+#define OZ_CASE(B, W, A_, C_) if (bk == B && bn == W && cm == A_ && cn == C_) \
+    return oz_launch_t<B, W, A_, C_>(mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc, st);
+  OZ_CASE(64, 64, 1, 1) OZ_CASE(64, 80, 1, 1) OZ_CASE(64, 96, 1, 1) OZ_CASE(64, 128, 1, 1) OZ_CASE(64, 160, 1, 1) OZ_CASE(64, 256, 1, 1)
+  OZ_CASE(128, 64, 1, 1) OZ_CASE(128, 128, 1, 1) OZ_CASE(128, 160, 1, 1) OZ_CASE(128, 256, 1, 1)
+  // cluster (TMA multicast) variants, kept for the record: measured equal or slower (profiles/r01_ozaki_int8.md)
+  OZ_CASE(64, 64, 2, 2) OZ_CASE(64, 64, 1, 4) OZ_CASE(64, 64, 2, 1) OZ_CASE(64, 64, 1, 2)
 #undef OZ_CASE
   return MCACQ_EINVAL;
+}
+
+// Column-tile width: the widest multiple of 16 whose G int32 accumulator tiles fit the 512 TMEM columns (<= 256, the
+// UMMA / TMA box limit).
+static int oz_pick_bn(int G) {
+  int bn = (512 / G) / 16 * 16;
+  return bn > OZ_MAX_BN ? OZ_MAX_BN : bn;
 }
 
 }  // namespace mcacq
@@ -445,10 +480,12 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   if ((int64_t)K * 128 * 128 * G >= (int64_t)1 << 31) return MCACQ_ELIMIT;  // exact int32 accumulation of a diagonal
   if (M == 0) return 0;
   // 128-byte k-blocks (full L2 lines, SWIZZLE_128B) when at least two stages of them fit, else 64-byte k-blocks
-  const size_t smem_budget = 232448 - 2048 - 1024;  // 227 KB per CTA minus static shared memory and alignment slack
+  const size_t smem_budget = 232448 - 4096 - 1024;  // 227 KB per CTA minus static shared memory (column scales, barriers) and alignment slack
+  int bn = (getenv("MCACQ_OZ_BN") != nullptr) ? atoi(getenv("MCACQ_OZ_BN")) : oz_pick_bn(G);
+  if (bn < 16 || bn > OZ_MAX_BN || (bn % 16) != 0 || G * bn > 512) return MCACQ_EINVAL;
   int bk = (getenv("MCACQ_OZ_BK") != nullptr) ? atoi(getenv("MCACQ_OZ_BK")) : 0;
-  if (bk != 64 && bk != 128) bk = ((size_t)2 * G * (OZ_BM + OZ_BN) * 128 <= smem_budget) ? 128 : 64;
-  const size_t stage_bytes = (size_t)G * (OZ_BM + OZ_BN) * bk;
+  if (bk != 64 && bk != 128) bk = (bn != 80 && bn != 96 && (size_t)2 * G * (OZ_BM + bn) * 128 <= smem_budget) ? 128 : 64;
+  const size_t stage_bytes = (size_t)G * (OZ_BM + bn) * bk;
   int stages = (int)(smem_budget / stage_bytes);
   if (stages > OZ_MAX_STAGES) stages = OZ_MAX_STAGES;
   if (stages < 1) return MCACQ_ELIMIT;
@@ -456,12 +493,13 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   CUtensorMap mapA, mapB;
   int rc;
   if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk))) return rc;
-  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, OZ_BN, bk))) return rc;
+  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, bk))) return rc;
   // Cluster shape (rows x columns of CTA tiles sharing operand loads through TMA multicast).  Measured on B200
   // (profiles/r01_ozaki_int8.md): multicast halves the L2 reads but not the bytes delivered to each SM, which is what
   // bounds this kernel (~20 B/clk/SM, ~5.8 TB/s chip-wide), so 1x1 is the default; 2x1 / 1x2 tie, 2x2 is 13% slower.
   int cm = 1, cn = 1;
   if (getenv("MCACQ_OZ_CLUSTER") != nullptr) { int v = atoi(getenv("MCACQ_OZ_CLUSTER")); cm = v / 10; cn = v % 10; }
-  return oz_launch(bk, cm, cn, mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
+  if (cm * cn > 1 && (bn != 64 || bk != 64)) return MCACQ_EINVAL;
+  return oz_launch(bk, bn, cm, cn, mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
                    (cudaStream_t)stream);
 }
