@@ -33,9 +33,25 @@ __device__ __forceinline__ void load4(const double* p, bool ok, double (&v)[4]) 
 }
 
 
+template <int N>
+__device__ __forceinline__ void loadn(const double* p, bool ok, double (&v)[N]) {
+  static_assert(N == 2 || N == 4, "fragment width");
+  if (ok) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    v[0] = a.x; v[1] = a.y;
+    if (N == 4) {
+      double2 b = *reinterpret_cast<const double2*>(p + 2);
+      v[2] = b.x; v[3] = b.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = 0.0;
+  }
+}
+
 constexpr int BLK_WARPS = 4;
 
-template <int QT, int RT, int NB>
+template <int QT, int RT, int NB, bool MEAN>
 __global__ void __launch_bounds__(BLK_WARPS * 32)
 posterior_blocks_kernel(BlocksParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -60,46 +76,62 @@ posterior_blocks_kernel(BlocksParams p) {
       for (int nj = 0; nj < (RT > 0 ? RT : 1); nj++) { accB[nb][mi][nj][0] = 0.0; accB[nb][mi][nj][1] = 0.0; }
     }
 
-  for (int k0 = 0; k0 < np; k0 += 16) {
-    const int kc = k0 + 4 * t4;
-    double al[4];
-    load4(p.alpha + kc, true, al);
-    double bf[RT > 0 ? RT : 1][4];
+  // Software-pipelined sweep: every A fragment register is re-loaded for the NEXT 16-column step right after its last
+  // use in the current one, so a full step of DMMAs (NB batches) covers the latency of each 32-byte load without any
+  // extra registers.
+  double af[NB][QT][4];
+  double kf[MEAN ? NB : 1][QT][4];
+  double bf[RT > 0 ? RT : 1][4];
+  double al[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t off0 = (b0 * q + g) * (int64_t)np + 4 * t4;   // fragment (nb, mi) starts at off0 + (nb * q + 8 * mi) * np
+  const int64_t bstride = (int64_t)q * np;
 #pragma unroll
-    for (int nj = 0; nj < RT; nj++) {
-      int row = nj * 8 + g;
-      load4(p.A_base + (int64_t)row * np + kc, row < r, bf[nj]);
+  for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      const bool ok = (b0 + nb < p.b) && mi * 8 + g < q;
+      load4(p.A + off0 + nb * bstride + (int64_t)mi * 8 * np, ok, af[nb][mi]);
+      if (MEAN) load4(p.Kt + off0 + nb * bstride + (int64_t)mi * 8 * np, ok, kf[nb][mi]);
     }
 #pragma unroll
+  for (int nj = 0; nj < RT; nj++) load4(p.A_base + (int64_t)(nj * 8 + g) * np + 4 * t4, nj * 8 + g < r, bf[nj]);
+  if (MEAN) load4(p.alpha + 4 * t4, true, al);
+
+  for (int k0 = 0; k0 < np; k0 += 16) {
+    const bool more = k0 + 16 < np;
+#pragma unroll
     for (int nb = 0; nb < NB; nb++) {
-      const int64_t bb = b0 + nb;
-      const bool bok = bb < p.b;
-      double af[QT][4];
 #pragma unroll
       for (int mi = 0; mi < QT; mi++) {
-        int i = mi * 8 + g;
-        bool ok = bok && i < q;
-        int64_t row = bb * q + i;
-        load4(p.A + row * np + kc, ok, af[mi]);
-        if (p.Kt != nullptr) {
-          double kf[4];
-          load4(p.Kt + row * np + kc, ok, kf);
+        if (MEAN) {
 #pragma unroll
-          for (int s = 0; s < 4; s++) macc[nb][mi] = fma(kf[s], al[s], macc[nb][mi]);
+          for (int s = 0; s < 4; s++) macc[nb][mi] = fma(kf[nb][mi][s], al[s], macc[nb][mi]);
+          load4(p.Kt + off0 + nb * bstride + (int64_t)mi * 8 * np + k0 + 16, more && (b0 + nb < p.b) && mi * 8 + g < q,
+                kf[nb][mi]);
         }
 #pragma unroll
-        for (int s = 0; s < 4; s++) amax[nb][mi] = fmax(amax[nb][mi], fabs(af[mi][s]));
+        for (int s = 0; s < 4; s++) amax[nb][mi] = fmax(amax[nb][mi], fabs(af[nb][mi][s]));
       }
 #pragma unroll
       for (int s = 0; s < 4; s++)
 #pragma unroll
         for (int mi = 0; mi < QT; mi++) {
 #pragma unroll
-          for (int nj = 0; nj <= mi; nj++) dmma884b(accG[nb][mi][nj][0], accG[nb][mi][nj][1], af[mi][s], af[nj][s]);
+          for (int nj = 0; nj <= mi; nj++)
+            dmma884b(accG[nb][mi][nj][0], accG[nb][mi][nj][1], af[nb][mi][s], af[nb][nj][s]);
 #pragma unroll
-          for (int nj = 0; nj < RT; nj++) dmma884b(accB[nb][mi][nj][0], accB[nb][mi][nj][1], af[mi][s], bf[nj][s]);
+          for (int nj = 0; nj < RT; nj++) dmma884b(accB[nb][mi][nj][0], accB[nb][mi][nj][1], af[nb][mi][s], bf[nj][s]);
         }
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++)
+        load4(p.A + off0 + nb * bstride + (int64_t)mi * 8 * np + k0 + 16, more && (b0 + nb < p.b) && mi * 8 + g < q,
+              af[nb][mi]);
     }
+    // the baseline fragments are shared by all batches of the step (L2-resident r x np panel): reload after the last use
+#pragma unroll
+    for (int nj = 0; nj < RT; nj++)
+      load4(p.A_base + (int64_t)(nj * 8 + g) * np + k0 + 16 + 4 * t4, more && nj * 8 + g < r, bf[nj]);
+    if (MEAN) load4(p.alpha + k0 + 16 + 4 * t4, more, al);
   }
 
   const double s2 = p.y_std * p.y_std;
@@ -222,52 +254,77 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
   }
   const size_t slice_stride = (size_t)p.b * q * np;
   double* Ab = p.A + bb * q * np;
-#pragma unroll 2
-  for (int c0 = 0; c0 < np; c0 += 16) {
-    const int cc = c0 + 2 * g;  // this lane's two source columns
-    double acc[QT][2][2];
+  // 8 * NT output columns per step as NT DMMA column tiles (NT = 4 for the small shapes, 2 when the coefficient
+  // fragments already fill the register file).  Lane (g, t4) loads columns c0 + NT g .. + NT-1 of source row
+  // j = 4 kk + t4; tile t takes column NT n + t as its B column n, so the lane ends up with the 2 NT CONSECUTIVE output
+  // columns c0 + 2 NT t4 .. of row g (acc[.][t][e] <-> column 2 NT t4 + NT e + t): 64-byte fp64 stores / 8-byte slice
+  // stores at NT = 4.  The source fragments are re-loaded for the next step right after their last DMMA (software
+  // pipelining without extra registers); the in-place dA store only touches columns of the current step.
+  constexpr int NT = (QT == 1 && RT <= 4) ? 4 : 2;
+  double rq[2 * QT][NT];
+  double rb[RT > 0 ? 2 * RT : 1][NT];
 #pragma unroll
-    for (int mi = 0; mi < QT; mi++) { acc[mi][0][0] = acc[mi][0][1] = acc[mi][1][0] = acc[mi][1][1] = 0.0; }
-    double2 rq[2 * QT];
+  for (int kk = 0; kk < 2 * QT; kk++) loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + NT * g, kk * 4 + t4 < q && NT * g < np, rq[kk]);
 #pragma unroll
-    for (int kk = 0; kk < 2 * QT; kk++) {
-      const int j = kk * 4 + t4;
-      rq[kk] = (j < q) ? *reinterpret_cast<const double2*>(Ab + (int64_t)j * np + cc) : make_double2(0.0, 0.0);
-    }
+  for (int kk = 0; kk < 2 * RT; kk++)
+    loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + NT * g, kk * 4 + t4 < r && NT * g < np, rb[kk]);
+  for (int c0 = 0; c0 < np; c0 += 8 * NT) {
+    const int cn = c0 + 8 * NT + NT * g;  // this lane's source columns in the next step
+    double acc[QT][NT][2];
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++)
+#pragma unroll
+      for (int t = 0; t < NT; t++) { acc[mi][t][0] = 0.0; acc[mi][t][1] = 0.0; }
 #pragma unroll
     for (int kk = 0; kk < 2 * RT; kk++) {
-      const int j = kk * 4 + t4;
-      double2 rb = (j < r) ? *reinterpret_cast<const double2*>(p.A_base + (int64_t)j * np + cc) : make_double2(0.0, 0.0);
 #pragma unroll
-      for (int mi = 0; mi < QT; mi++) {
-        dmma884b(acc[mi][0][0], acc[mi][0][1], cb[mi][kk], rb.x);
-        dmma884b(acc[mi][1][0], acc[mi][1][1], cb[mi][kk], rb.y);
-      }
+      for (int mi = 0; mi < QT; mi++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cb[mi][kk], rb[kk][t]);
+      loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < r && cn < np, rb[kk]);
     }
 #pragma unroll
-    for (int kk = 0; kk < 2 * QT; kk++)
+    for (int kk = 0; kk < 2 * QT; kk++) {
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cq[mi][kk], rq[kk][t]);
+      loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < q && cn < np, rq[kk]);
+    }
+    // every lane of the warp has issued its loads of this step's columns (they were fetched one step earlier) before
+    // any lane overwrites them in place
+    __syncwarp();
+    const int oc = c0 + 2 * NT * t4;
+    if (oc < np) {
 #pragma unroll
       for (int mi = 0; mi < QT; mi++) {
-        dmma884b(acc[mi][0][0], acc[mi][0][1], cq[mi][kk], rq[kk].x);
-        dmma884b(acc[mi][1][0], acc[mi][1][1], cq[mi][kk], rq[kk].y);
-      }
-    // tile0 column n <-> actual c0 + 2n, tile1 <-> c0 + 2n + 1: lane holds actual columns c0+4*t4 .. +3
-    __syncwarp();
+        const int i = mi * 8 + g;
+        if (i < q) {
+          if (p.emit_slices) {
+            unsigned long long Y[2][4];   // NT = 4: [e][t];  NT = 2: Y[0] = the lane's 4 columns
 #pragma unroll
-    for (int mi = 0; mi < QT; mi++) {
-      const int i = mi * 8 + g;
-      if (i < q) {
-        if (p.emit_slices) {
-          const unsigned long long Y[4] = {balanced_bytes(__double2ll_rn(ldexp(acc[mi][0][0], shift[mi]))),
-                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][1][0], shift[mi]))),
-                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][0][1], shift[mi]))),
-                                           balanced_bytes(__double2ll_rn(ldexp(acc[mi][1][1], shift[mi])))};
-          int8_t* sdst = p.slices + ((size_t)(bb * q + i)) * np + c0 + 4 * t4;
-          for (int pp = 0; pp < p.G; pp++) *reinterpret_cast<unsigned*>(sdst + pp * slice_stride) = pack_digit4(Y, p.G - 1 - pp);
-        } else {
-          double* dst = Ab + (int64_t)i * np + c0 + 4 * t4;
-          *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][0][0], acc[mi][1][0]);
-          *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[mi][0][1], acc[mi][1][1]);
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                const unsigned long long y = balanced_bytes(__double2ll_rn(ldexp(acc[mi][t][e], shift[mi])));
+                if (NT == 4) Y[e][t] = y; else Y[0][e * 2 + t] = y;
+              }
+            int8_t* sdst = p.slices + ((size_t)(bb * q + i)) * np + oc;
+            for (int pp = 0; pp < p.G; pp++) {
+              if (NT == 4)
+                *reinterpret_cast<uint2*>(sdst + pp * slice_stride) =
+                    make_uint2(pack_digit4(Y[0], p.G - 1 - pp), pack_digit4(Y[1], p.G - 1 - pp));
+              else
+                *reinterpret_cast<unsigned*>(sdst + pp * slice_stride) = pack_digit4(Y[0], p.G - 1 - pp);
+            }
+          } else {
+            double* dst = Ab + (int64_t)i * np + oc;
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int t = 0; t < NT; t += 2)
+                *reinterpret_cast<double2*>(dst + e * NT + t) = make_double2(acc[mi][t][e], acc[mi][t + 1][e]);
+          }
         }
       }
     }
@@ -307,7 +364,8 @@ static int launch_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
   constexpr int NB = (QT == 1 && RT <= 4) ? 4 : 1;
   int64_t per_cta = (int64_t)BLK_WARPS * NB;
   int64_t blocks = (p.b + per_cta - 1) / per_cta;
-  posterior_blocks_kernel<QT, RT, NB><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  if (p.Kt != nullptr) posterior_blocks_kernel<QT, RT, NB, true><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  else posterior_blocks_kernel<QT, RT, NB, false><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

@@ -168,7 +168,7 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
                      const double* __restrict__ row_scale, const double* __restrict__ col_vec,
                      double* __restrict__ dU1, int accumulate) {
   constexpr int DP = 8 * NTD;
-  extern __shared__ __align__(32) double sm[];
+  extern __shared__ __align__(16) double sm[];
   double* s1 = sm;                         // [d][BW_T]      U1^T tile (rows of this CTA)
   double* s2 = s1 + (size_t)d * BW_T;      // [DP][BW_P]     [U2 | 1 | 0]^T tile
   double* sG = s2 + (size_t)DP * BW_P;     // [BW_T][BW_P]   G tile; reused for V at the end
@@ -206,6 +206,27 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
       int gc = c0 + p;
       sc[p] = (col_vec != nullptr && gc < m2) ? col_vec[gc] : 0.0;
     }
+    // the 4 x 4 block of upstream gradients W is requested before the barrier and the distance loop so that its HBM
+    // latency is covered by them
+    double w[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t gr = row0 + ty * 4 + i;
+      const int gc0 = c0 + tx * 4;
+#pragma unroll
+      for (int j = 0; j < 4; j++) w[i][j] = 0.0;
+      if (gr < m1) {
+        const double* wp = W + gr * ldw + gc0;
+        if (gc0 + 3 < m2 && ((ldw & 1) == 0)) {
+          double2 w01 = *reinterpret_cast<const double2*>(wp);
+          double2 w23 = *reinterpret_cast<const double2*>(wp + 2);
+          w[i][0] = w01.x; w[i][1] = w01.y; w[i][2] = w23.x; w[i][3] = w23.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) if (gc0 + j < m2) w[i][j] = wp[j];
+        }
+      }
+    }
     __syncthreads();
     // ---- phase 1
     double sq[4][4];
@@ -230,24 +251,12 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
     for (int i = 0; i < 4; i++) {
       const int64_t gr = row0 + ty * 4 + i;
       const int gc0 = c0 + tx * 4;
-      double w[4] = {0.0, 0.0, 0.0, 0.0};
-      if (gr < m1) {
-        const double* wp = W + gr * ldw + gc0;
-        if (gc0 + 3 < m2 && ((ldw & 1) == 0)) {
-          double2 w01 = *reinterpret_cast<const double2*>(wp);
-          double2 w23 = *reinterpret_cast<const double2*>(wp + 2);
-          w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++) if (gc0 + j < m2) w[j] = wp[j];
-        }
-      }
       const double rs = sr[ty * 4 + i];
       double gv[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const bool ok = (gr < m1) && (gc0 + j < m2);
-        gv[j] = ok ? (w[j] + rs * sc[tx * 4 + j]) * kernel_dfactor(kernel_id, outputscale, sq[i][j]) : 0.0;
+        gv[j] = ok ? (w[i][j] + rs * sc[tx * 4 + j]) * kernel_dfactor(kernel_id, outputscale, sq[i][j]) : 0.0;
       }
       *reinterpret_cast<double4*>(sG + (ty * 4 + i) * BW_P + tx * 4) = make_double4(gv[0], gv[1], gv[2], gv[3]);
     }

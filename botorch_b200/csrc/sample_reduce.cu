@@ -289,6 +289,7 @@ sample_reduce_fwd_kernel(SRParams p) {
     for (int ns = 0; ns < NS; ns++)
 #pragma unroll
       for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+#pragma unroll 4
     for (int j = 0; j < r + q; j++) {
       double z[NS];
 #pragma unroll
@@ -402,6 +403,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
       for (int ns = 0; ns < NS; ns++)
 #pragma unroll
         for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+#pragma unroll 4
       for (int j = 0; j < r + q; j++) {
         double z[NS];
 #pragma unroll
@@ -467,16 +469,26 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
         double acc[MT][2];
 #pragma unroll
         for (int mi = 0; mi < MT; mi++) { acc[mi][0] = 0.0; acc[mi][1] = 0.0; }
-        for (int kk = k_begin; kk < k_end; kk++) {
-          const int sl = 4 * kk + t4;
-          const double bv = (zr != nullptr) ? ((sl < nloc) ? zr[sl] : 0.0) : bconst;
+        // four k-steps per trip with all operand loads issued first (the base samples come straight from L2)
+        for (int kk = k_begin; kk < k_end; kk += 4) {
+          double bv[4], av[4][MT];
 #pragma unroll
-          for (int mi = 0; mi < MT; mi++) {
-            const int i = mi * 8 + g;
-            const double av = (i < q) ? gy[(size_t)sl * GP + i] : 0.0;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                         : "+d"(acc[mi][0]), "+d"(acc[mi][1]) : "d"(av), "d"(bv));
+          for (int u = 0; u < 4; u++) {
+            const int sl = 4 * (kk + u) + t4;
+            const bool live = (kk + u < k_end) && sl < nloc;
+            bv[u] = (zr != nullptr) ? (live ? zr[sl] : 0.0) : ((kk + u < k_end) ? bconst : 0.0);
+#pragma unroll
+            for (int mi = 0; mi < MT; mi++) {
+              const int i = mi * 8 + g;
+              av[u][mi] = (live && i < q) ? gy[(size_t)sl * GP + i] : 0.0;
+            }
           }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int mi = 0; mi < MT; mi++)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                           : "+d"(acc[mi][0]), "+d"(acc[mi][1]) : "d"(av[u][mi]), "d"(bv[u]));
         }
 #pragma unroll
         for (int mi = 0; mi < MT; mi++) {
