@@ -294,11 +294,12 @@ def main():
             # dense int8 peak of the part = 2 x the measured dense bf16 peak
             peak_equiv = 2.0 * bf16_peak / pairs
             return {"bound": "tensor", "kernel": "ozaki_imma_kernel (tcgen05 kind::i8, G=6 forward launch)", "achieved": ach,
-                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": None,
+                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.59e9 * (M / 65536.0),
                     "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
                     "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
                     "fp64_dgemm_peak_measured": fp64_peak_tf,
-                    "traffic_source": "see profiles/r01_ozaki_int8.md (10.4 GB per launch measured for the 7-slice version)"}
+                    "traffic_source": "ncu --set full dram__bytes_read+write of the forward launch at M=65536 (6.47 + 2.12 GB, "
+                                      "profiles/r01_ncu_full_int8_mode.md; algorithmic: 1.7 GB slices + 2.15 GB output), scaled to this M"}
 
         roof = {"int8": int8_roofline, "dmma": dmma_roofline}
         roofline = roof[args.contraction]()
