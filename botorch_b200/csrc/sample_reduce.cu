@@ -13,6 +13,7 @@
 // (same weights as botorch/csrc/logei_fused.cpp:109-111, 143-174), contracts them with
 // the base samples, and runs the q x q Cholesky reverse-mode and the triangular-solve reverse-mode in
 // shared memory.
+#include <cstdlib>
 #include "common.cuh"
 #include "params.cuh"
 #include <math_constants.h>
@@ -629,16 +630,18 @@ static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
 int sample_reduce_fwd(const SRParams& p, cudaStream_t st) {
   if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
   if (p.b == 0) return 0;
-  if (p.q <= 8) return launch_sr_fwd<8, 4>(p, st);
-  if (p.q <= 16) return launch_sr_fwd<16, 2>(p, st);
+  // one sample per thread and pass: more resident warps beat per-thread ILP here (the transcendental chains do not
+  // interleave across samples): 1.55 -> 0.96 ms forward, 2.86 -> 1.83 ms backward per C3 chunk
+  if (p.q <= 8) return launch_sr_fwd<8, 1>(p, st);
+  if (p.q <= 16) return launch_sr_fwd<16, 1>(p, st);
   return launch_sr_fwd<32, 1>(p, st);
 }
 
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st) {
   if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
   if (p.b == 0) return 0;
-  if (p.q <= 8) return launch_sr_bwd<8, 4>(p, st);
-  if (p.q <= 16) return launch_sr_bwd<16, 2>(p, st);
+  if (p.q <= 8) return launch_sr_bwd<8, 1>(p, st);
+  if (p.q <= 16) return launch_sr_bwd<16, 1>(p, st);
   return launch_sr_bwd<32, 1>(p, st);
 }
 
