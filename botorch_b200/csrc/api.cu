@@ -151,6 +151,8 @@ extern "C" int mcacq_posterior(const mcacq_model* model, const double* X, int64_
                                double* covar, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_model(model);
   if (rc) return rc;
+  if (b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (b == 0) return 0;  // empty t-batch: nothing to launch, the (possibly null) pointers are never touched
   if (!X || !mean || !covar || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   if (b == 0) return 0;
@@ -206,6 +208,8 @@ extern "C" int mcacq_posterior_backward(const mcacq_model* model, const double* 
                                         size_t workspace_bytes, void* stream) {
   int rc = check_model(model);
   if (rc) return rc;
+  if (b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (b == 0) return 0;  // empty t-batch: nothing to launch, the (possibly null) pointers are never touched
   if (!X || !gmean || !gcovar || !grad_X || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   if (b == 0) return 0;
@@ -240,6 +244,8 @@ extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline*
   int rc = check_model(model);
   if (rc) return rc;
   if ((rc = check_mc(mc))) return rc;
+  if (b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (b == 0) return 0;  // empty t-batch: nothing to launch, the (possibly null) pointers are never touched
   if (!X || !acq || !info || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   const int r = base ? base->r : 0;
@@ -264,6 +270,8 @@ extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline
   int rc = check_model(model);
   if (rc) return rc;
   if ((rc = check_mc(mc))) return rc;
+  if (b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (b == 0) return 0;  // empty t-batch: nothing to launch, the (possibly null) pointers are never touched
   if (!X || !acq || !grad_acq || !grad_X || !workspace || b < 0 || q <= 0) return MCACQ_EINVAL;
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   const int r = base ? base->r : 0;

@@ -171,7 +171,7 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
   extern __shared__ __align__(16) double sm[];
   double* s1 = sm;                         // [d][BW_T]      U1^T tile (rows of this CTA)
   double* s2 = s1 + (size_t)d * BW_T;      // [DP][BW_P]     [U2 | 1 | 0]^T tile
-  double* sG = s2 + (size_t)DP * BW_P;     // [BW_T][BW_P]   G tile; reused for V at the end
+  double* sG = s2 + (size_t)DP * BW_P;     // [BW_T][BW_P]   G tile
   double* sc = sG + (size_t)BW_T * BW_P;   // [BW_T] col_vec tile
   double* sr = sc + BW_T;                  // [BW_T] row_scale
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,7 +273,7 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
   }
   __syncthreads();
   // ---- finalize: V -> shared, dU1[row][k] = u1[row][k] * rowsum[row] - V[row][k]
-  double* sV = sG;  // [BW_T][DP]
+  double* sV = s2;  // [BW_T][DP]: reuses the (now idle) operand tile AND the G tile behind it -- DP can exceed BW_P (d = 64)
 #pragma unroll
   for (int j = 0; j < NTD; j++) {
     sV[(warp * 8 + g) * DP + j * 8 + 2 * t4] = vacc[j][0];

@@ -122,6 +122,43 @@ class DevicePredictionStrategy:
             R_slices=_lib.ptr(self.R_slices), R_scale=_lib.ptr(self.R_scale),
         )
 
+        if contraction == "int8":
+            self._guard_int8(Xt)
+
+    # The slices are FIXED-point relative to each row's largest entry: the int8 contraction reproduces the posterior
+    # variance to ~1e-12 of the PRIOR variance (measured 3e-13 .. 9e-13 on C1-C3), i.e. to 1e-8 .. 1e-11 of the variance
+    # itself depending on how far it has collapsed (1.2e-8 AT the C3 training points, 5e-11 in the rest of the box).
+    # When K is so ill-conditioned that the variance collapses by more than ~5 orders of magnitude everywhere, the digits
+    # the fp64 contraction keeps are lost: the probe below detects that and switches the model to 'dmma'.
+    INT8_PROBE_TOL = 1e-7
+
+    def _guard_int8(self, Xt: Tensor) -> None:
+        """Probe the int8 contraction against the FP64 one on this model (training points: smallest posterior variances,
+        hence the worst cancellation; plus uniform points of their bounding box) and fall back to 'dmma' when the
+        posterior variance differs by more than INT8_PROBE_TOL (relative, pointwise)."""
+        n = Xt.shape[0]
+        take = torch.linspace(0, n - 1, min(n, 256), device=Xt.device).round().long()
+        g = torch.Generator(device="cpu").manual_seed(0)
+        lo, hi = Xt.min(dim=0).values, Xt.max(dim=0).values
+        box = lo + (hi - lo) * torch.rand(256, self.d, generator=g, dtype=torch.float64).to(Xt.device)
+        probe = torch.cat([Xt[take], box]) * self.x_coef + self.x_offset  # back to the raw input space
+        probe = probe.unsqueeze(1)  # P x 1 x d
+        _, v8 = self.posterior_blocks(probe)
+        self.desc.contraction = 0
+        _, v64 = self.posterior_blocks(probe)
+        floor = 1e-8 * self.y_std * self.y_std * self.outputscale
+        err = float(((v8 - v64).abs() / v64.abs().clamp_min(floor)).max())
+        self.int8_probe_error = err
+        if err <= self.INT8_PROBE_TOL:
+            self.desc.contraction = 1
+            return
+        warnings.warn(f"int8 contraction disabled for this model: posterior variance differs by {err:.1e} (relative) from "
+                      "the FP64 contraction on the probe set (ill-conditioned train covariance); using 'dmma'.",
+                      NumericalWarning, stacklevel=3)
+        self.contraction = "dmma"
+        self.Rt_slices = self.Rt_scale = self.R_slices = self.R_scale = None
+        self.desc.Rt_slices = self.desc.Rt_scale = self.desc.R_slices = self.desc.R_scale = None
+
     def _slice_rows(self, Mx: Tensor, G: int = 6) -> tuple[Tensor, Tensor]:
         rows, K = Mx.shape
         S = torch.empty(G, rows, K, dtype=torch.int8, device=self.device)
