@@ -261,7 +261,7 @@ sample_reduce_fwd_kernel(SRParams p) {
           for (int k = 0; k < j; k++) v -= Cs[lane * q + k] * Cs[j * q + k];
         }
         const double dj = __shfl_sync(0xffffffffu, v, j);
-        if (!(dj > 0.0)) { ok = false; break; }
+        if (!(dj > 0.0)) { ok = false; __syncwarp(); break; }  // (orders this attempt's reads before the retry's writes)
         const double sj = sqrt(dj);
         if (lane >= j && lane < q) Cs[lane * q + j] = (lane == j) ? sj : v / sj;
         __syncwarp();

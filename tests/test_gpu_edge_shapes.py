@@ -42,6 +42,8 @@ SHAPES = [
     (50, 5, 5, 64, 32, 2, "matern52"),  # maximum r
     (100, 2, 9, 17, 33, 7, "rbf"),      # odd q / r / S (26 jointly sampled points in the unit square: short lengthscale below)
     (130, 6, 17, 40, 24, 4, "matern52"),
+    (200, 8, 32, 64, 16, 2, "matern52"),  # maximum q AND maximum r (largest register / shared-memory variants)
+    (64, 4, 4, 8, 1000, 3, "rbf"),        # S not a multiple of the 128-thread sample pass
 ]
 
 
@@ -133,3 +135,30 @@ def test_int8_guard_falls_back_on_ill_conditioned_models():
         assert strat.contraction == "int8" and strat.int8_probe_error <= strat.INT8_PROBE_TOL
     finally:
         settings.contraction.set("dmma")
+
+
+def test_chunk_boundary_is_invisible():
+    """b * q beyond the 2^17-row workspace chunk: the host splits the t-batch; results must equal the pieces evaluated alone
+    (bitwise) and the oracle on a sample of rows."""
+    from botorch_b200.acquisition import qLogNoisyExpectedImprovement
+    from botorch_b200.sampling import SobolQMCNormalSampler
+    from oracle.acquisition import OracleQLogNEI, value_and_grad
+
+    model, gp, X, Y, g = _pair(64, 3, "matern52", 21, "dmma")
+    Xb = torch.rand(5, 3, generator=g, dtype=torch.float64)
+    acqf = qLogNoisyExpectedImprovement(model, X_baseline=Xb.to(DEV), prune_baseline=False,
+                                        sampler=SobolQMCNormalSampler(torch.Size([32]), seed=3))
+    b, q = 33000, 4  # 132000 rows: one full chunk of 32768 q-batches + a ragged tail of 232
+    Xq = torch.rand(b, q, 3, generator=g, dtype=torch.float64).to(DEV)
+    Xg = Xq.clone().requires_grad_(True)
+    v = acqf(Xg)
+    (gr,) = torch.autograd.grad(v.sum(), Xg)
+    for lo, hi in ((0, 32768), (32768, b)):
+        Xp = Xq[lo:hi].clone().requires_grad_(True)
+        vp = acqf(Xp)
+        (gp_,) = torch.autograd.grad(vp.sum(), Xp)
+        assert torch.equal(vp.detach(), v.detach()[lo:hi]) and torch.equal(gp_, gr[lo:hi])
+    idx = torch.tensor([0, 1, 32767, 32768, 32769, b - 1])
+    v_o, g_o = value_and_grad(OracleQLogNEI(gp, Xb, 32, 3), Xq[idx].cpu())
+    assert float(((v.detach()[idx].cpu() - v_o).abs() / v_o.abs()).max()) < 1e-8
+    assert float((gr[idx].cpu() - g_o).abs().max() / g_o.abs().max()) < 1e-6

@@ -157,7 +157,7 @@ def test_mock_style_bounds_qlogei():
         qLogExpectedImprovement(model, best_f=0.0, tau_relu=-1.0)
 
 
-@pytest.mark.parametrize("cfg,n,b", [("C1", None, 64), ("C2", None, 40), ("C3", 1100, 24), ("C3", None, 64)])
+@pytest.mark.parametrize("cfg,n,b", [("C1", None, 64), ("C2", None, 40), ("C3", 1100, 24), ("C3", 2500, 16), ("C3", None, 64)])
 def test_int8_contraction_mode_parity(cfg, n, b):
     """Same parity bar with the contraction on the INT8 tensor cores (Ozaki split, tcgen05): values 1e-9, grads 1e-7,
     posterior mean/variance 1e-9."""
