@@ -190,10 +190,12 @@ class SingleTaskGP(Model):
         batch_shape, q, d = X.shape[:-2], X.shape[-2], X.shape[-1]
         Xf = X.reshape(-1, q, d).to(device=strat.device, dtype=torch.float64)
         if q > _lib.MAX_Q:
-            # large joint posteriors (baseline sets, candidate sets): setup-time route, no gradient
+            # large joint posteriors (baseline sets, candidate sets, cat[X, X_baseline] of the generic qLogNEI route when
+            # r exceeds the fused kernels' limit): one point set at a time through the covariance / contraction kernels
             if X.requires_grad and torch.is_grad_enabled():
-                raise UnsupportedError(f"Gradients through joint posteriors over q > {_lib.MAX_Q} points are not supported.")
-            ms, cs = zip(*(strat.joint_posterior(x) for x in Xf))
+                ms, cs = zip(*(strat.joint_posterior_with_grad(x) for x in Xf))
+            else:
+                ms, cs = zip(*(strat.joint_posterior(x) for x in Xf))
             mean, covar = torch.stack(ms), torch.stack(cs)
         else:
             mean, covar = self._posterior_chunks(Xf, strat)

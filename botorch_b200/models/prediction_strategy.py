@@ -236,6 +236,11 @@ class DevicePredictionStrategy:
         covar = (self.y_std**2) * (Kxx - G)
         return mean, covar
 
+    def joint_posterior_with_grad(self, X: Tensor) -> tuple[Tensor, Tensor]:
+        """Differentiable `joint_posterior` (N x d -> mean [N], covar [N x N]) for joint posteriors beyond the fused kernels'
+        q limit, e.g. the generic qLogNEI route over cat[X, X_baseline] when r > MCACQ_MAX_R."""
+        return _JointPosterior.apply(X, self)
+
     def lower_times_samples(self, chol: Tensor, Z: Tensor) -> Tensor:
         """Y[N x S] = L[N x N] Z[S x N]^T with the triangular-aware DMMA kernel (MultivariateNormal.rsample's
         `root @ base_samples`)."""
@@ -249,3 +254,58 @@ class DevicePredictionStrategy:
         _lib.check(_lib.lib().mcacq_dgemm_nt(1, N, S, N, chol.data_ptr(), N, Z.data_ptr(), N, Y.data_ptr(), S,
                                              counter.data_ptr(), _lib.stream_ptr()), "dgemm_nt (trmm)")
         return Y
+
+
+class _JointPosterior(torch.autograd.Function):
+    """Joint posterior over N points with a hand-assembled backward from the same C entry points as the fused path:
+    dA = -s^2 (G + G^T) A,  dKt = dA R^T (+ s gmean alpha^T inside the covariance backward),  dU from `mcacq_cov_cross_bwd`
+    against the train inputs and against the points themselves (the K(X, X) term).  Setup-time / fallback route: the two
+    N x N products are library matmuls."""
+
+    @staticmethod
+    def forward(ctx, X: Tensor, strat: "DevicePredictionStrategy"):
+        Xc = X.detach().to(device=strat.device, dtype=torch.float64).reshape(-1, strat.d).contiguous()
+        N = Xc.shape[0]
+        L, st = _lib.lib(), _lib.stream_ptr()
+        f64 = dict(device=strat.device, dtype=torch.float64)
+        U = strat.scale(Xc)
+        Kt = torch.empty(N, strat.np, **f64)
+        _lib.check(L.mcacq_cov_cross(strat.kernel_id, strat.outputscale, U.data_ptr(), N, strat.U_train.data_ptr(), strat.n,
+                                     strat.d, Kt.data_ptr(), strat.np, st), "cov_cross")
+        A = torch.empty(N, strat.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=strat.device)
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, N, strat.np, Kt.data_ptr(), strat.R.data_ptr(), A.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        Kxx = torch.empty(N, N, **f64)
+        _lib.check(L.mcacq_cov_cross(strat.kernel_id, strat.outputscale, U.data_ptr(), N, U.data_ptr(), N, strat.d,
+                                     Kxx.data_ptr(), N, st), "cov_cross")
+        mean = strat.y_mean + strat.y_std * (strat.mean_const + Kt @ strat.alpha)
+        covar = (strat.y_std**2) * (Kxx - A @ A.mT)
+        ctx.strat = strat
+        ctx.save_for_backward(U, A)
+        return mean, covar
+
+    @staticmethod
+    def backward(ctx, gmean: Tensor, gcovar: Tensor):
+        U, A = ctx.saved_tensors
+        strat = ctx.strat
+        N = U.shape[0]
+        L, st = _lib.lib(), _lib.stream_ptr()
+        f64 = dict(device=strat.device, dtype=torch.float64)
+        gm = torch.zeros(N, **f64) if gmean is None else gmean.to(**f64).contiguous()
+        gc = torch.zeros(N, N, **f64) if gcovar is None else gcovar.to(**f64)
+        s2 = strat.y_std**2
+        Gs = (s2 * (gc + gc.mT)).contiguous()
+        dA = -(Gs @ A).contiguous()
+        dKt = torch.empty(N, strat.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=strat.device)
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_LOWER, N, strat.np, dA.data_ptr(), strat.Rt.data_ptr(), dKt.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        rs = (strat.y_std * gm).contiguous()
+        dU = torch.empty(N, strat.d, **f64)
+        _lib.check(L.mcacq_cov_cross_bwd(strat.kernel_id, strat.outputscale, U.data_ptr(), N, strat.U_train.data_ptr(), strat.n,
+                                         strat.d, dKt.data_ptr(), strat.np, rs.data_ptr(), strat.alpha.data_ptr(),
+                                         dU.data_ptr(), 0, st), "cov_cross_bwd(train)")
+        _lib.check(L.mcacq_cov_cross_bwd(strat.kernel_id, strat.outputscale, U.data_ptr(), N, U.data_ptr(), N, strat.d,
+                                         Gs.data_ptr(), N, None, None, dU.data_ptr(), 1, st), "cov_cross_bwd(self)")
+        return dU / (strat.x_coef * strat.lengthscale), None

@@ -85,8 +85,8 @@ def test_edge_shapes_value_and_grad(n, d, q, r, S, b, kernel, contraction):
 
 
 def test_baseline_beyond_kernel_limit_takes_generic_route():
-    """r > MCACQ_MAX_R is outside the fused kernels: the host falls back to the generic sample-reducing route (posterior
-    blocks still from the CUDA kernels) instead of failing."""
+    """r > MCACQ_MAX_R is outside the fused kernels: the host falls back to the generic sample-reducing route, whose joint
+    posterior over cat[X, X_baseline] (and its gradient) is assembled from the covariance / contraction kernels."""
     from botorch_b200 import _lib
     from botorch_b200.acquisition import qLogNoisyExpectedImprovement
     from botorch_b200.sampling import SobolQMCNormalSampler
@@ -99,13 +99,24 @@ def test_baseline_beyond_kernel_limit_takes_generic_route():
                                         sampler=SobolQMCNormalSampler(torch.Size([16]), seed=3))
     Xq = torch.rand(3, 2, 3, generator=g, dtype=torch.float64)
     v_o, g_o = value_and_grad(OracleQLogNEI(gp, Xb, 16, 3), Xq)
-    with torch.no_grad():
-        v = acqf(Xq.to(DEV))
-    assert float(((v.cpu() - v_o).abs() / v_o.abs()).max()) < 1e-7
-    # gradients through a joint posterior over more than MAX_Q points are not built: loud, typed failure
-    from botorch_b200.exceptions import UnsupportedError
-    with pytest.raises(UnsupportedError):
-        acqf(Xq.to(DEV).requires_grad_(True))
+    Xg = Xq.to(DEV).requires_grad_(True)
+    v = acqf(Xg)
+    (gr,) = torch.autograd.grad(v.sum(), Xg)
+    assert float(((v.detach().cpu() - v_o).abs() / v_o.abs()).max()) < 1e-7
+    assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max()) < 1e-5
+    # the joint posterior behind it (q + r = 72 points per t-batch) against the oracle, values and gradient
+    Xj = torch.cat([Xq, Xb.expand(3, r, 3)], dim=-2)
+    m_o, c_o = gp.posterior_mvn(Xj)
+    Xjg = Xj.to(DEV).requires_grad_(True)
+    post = model.posterior(Xjg)
+    assert float((post.mean.squeeze(-1).detach().cpu() - m_o).abs().max() / m_o.abs().max()) < 1e-9
+    assert float((post.distribution.covariance_matrix.detach().cpu() - c_o).abs().max() / c_o.abs().max()) < 1e-9
+    w = torch.randn(c_o.shape, generator=g, dtype=torch.float64)
+    Xjo = Xj.clone().requires_grad_(True)
+    m2, c2 = gp.posterior_mvn(Xjo)
+    (g_ref,) = torch.autograd.grad((c2 * w).sum() + m2.sum(), Xjo)
+    (g_dev,) = torch.autograd.grad((post.distribution.covariance_matrix * w.to(DEV)).sum() + post.mean.sum(), Xjg)
+    assert float((g_dev.cpu() - g_ref).abs().max() / g_ref.abs().max()) < 1e-8
 
 
 def test_int8_guard_falls_back_on_ill_conditioned_models():
