@@ -121,8 +121,9 @@ def test_error_conventions():
     acqf = qLogExpectedImprovement(model, best_f=0.0)
     with pytest.raises(ValueError):
         acqf(torch.rand(4, device=DEV, dtype=torch.float64))  # fewer than 2 dims (t_batch_mode_transform)
-    with pytest.raises(Exception):
-        acqf(torch.rand(2, 40, 4, device=DEV, dtype=torch.float64, requires_grad=True)).sum().backward()  # q > 32 w/ grad
+    Xbig = torch.rand(2, 40, 4, device=DEV, dtype=torch.float64, requires_grad=True)  # q > 32: generic route, with gradient
+    acqf(Xbig).sum().backward()
+    assert Xbig.grad.shape == Xbig.shape and torch.isfinite(Xbig.grad).all()
     out = acqf(torch.rand(3, 2, 4, device=DEV, dtype=torch.float64))
     assert out.shape == (3,)
     assert acqf.sampler is not None and acqf.sampler.sample_shape == torch.Size([512])  # lazy default sampler
