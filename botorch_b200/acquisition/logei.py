@@ -194,7 +194,9 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
         return val.view(view_shape).to(obj)
 
     def _compute_best_feasible_objective(self, samples: Tensor, obj: Tensor) -> Tensor:
-        return compute_best_feasible_objective(samples=samples, obj=obj, constraints=self._constraints)
+        return compute_best_feasible_objective(samples=samples, obj=obj, constraints=self._constraints, model=self.model,
+                                               objective=self.objective, posterior_transform=self.posterior_transform,
+                                               X_baseline=self.X_baseline)
 
     def _sample_forward(self, obj: Tensor) -> Tensor:
         return _log_improvement(Y=obj, best_f=self.compute_best_f(obj), tau=self.tau_relu, fat=self._fat)

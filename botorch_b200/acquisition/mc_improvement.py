@@ -18,6 +18,7 @@ def _use_plain_reductions(acqf) -> None:
     sample_dim = tuple(range(len(acqf.sample_shape)))
     acqf._sample_reduction = partial(torch.mean, dim=sample_dim)
     acqf._q_reduction = partial(torch.amax, dim=-1)
+    acqf._fat = False  # constraint weighting of the non-log family uses the plain sigmoid (reference monte_carlo.py:146-212)
 
 
 class qExpectedImprovement(qLogExpectedImprovement):

@@ -14,6 +14,7 @@ from torch import Tensor
 
 from ..exceptions.errors import UnsupportedError
 from ..sampling.base import MCSampler
+from ..utils.objective import compute_smoothed_feasibility_indicator
 from ..utils.transforms import concatenate_pending_points, is_ensemble, t_batch_mode_transform
 from .acquisition import AcquisitionFunction, MCSamplerMixin
 from .objective import IdentityMCObjective, MCAcquisitionObjective, PosteriorTransform
@@ -76,8 +77,13 @@ class SampleReducingMCAcquisitionFunction(MCAcquisitionFunction):
         ...
 
     def _apply_constraints(self, acqval: Tensor, samples: Tensor) -> Tensor:
+        """Weight the per-sample utility by the smoothed feasibility indicator (reference :322-348)."""
         if self._constraints is not None:
-            raise UnsupportedError("Outcome constraints are on the 'next' list of botorch_b200 (SURVEY.md section 8f N3).")
+            if not self._log and (acqval < 0).any():
+                raise ValueError("Constraint-weighting requires unconstrained acquisition values to be non-negative.")
+            ind = compute_smoothed_feasibility_indicator(constraints=self._constraints, samples=samples, eta=self._eta,
+                                                         log=self._log, fat=self._fat)
+            acqval = acqval.add(ind) if self._log else acqval.mul(ind)
         return acqval
 
 

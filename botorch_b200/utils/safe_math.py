@@ -104,3 +104,35 @@ def logdiffexp(log_a: Tensor, log_b: Tensor) -> Tensor:
     log_a, log_b = torch.broadcast_tensors(log_a, log_b)
     is_inf = log_b == -torch.inf
     return log_b + log1mexp(log_a - log_b.masked_fill(is_inf, 0.0))
+
+
+def log1pexp(x: Tensor) -> Tensor:
+    """log(1 + exp(x)) without overflow, switching form at x = 18 (reference :84-93)."""
+    small = x <= 18
+    lo = x.masked_fill(~small, 0).exp().log1p()
+    hi_arg = x.masked_fill(small, 0)
+    return torch.where(small, lo, hi_arg + (-hi_arg).exp())
+
+
+def logexpit(X: Tensor) -> Tensor:
+    """log sigmoid(X) (reference :96-98)."""
+    return -log1pexp(-X)
+
+
+_INV_SQRT_3 = math.sqrt(1 / 3)
+
+
+def fatmoid(X: Tensor, tau=1.0) -> Tensor:
+    """Fat-tailed smooth step, O(1/x^2) as x -> -inf, inflection at 1/sqrt(3) (reference :441-458)."""
+    u = X / tau
+    return torch.where(u < 0, 2 / 3 * cauchy(u - _INV_SQRT_3), 1 - 2 / 3 * cauchy(u + _INV_SQRT_3))
+
+
+def log_fatmoid(X: Tensor, tau=1.0) -> Tensor:
+    return fatmoid(X, tau=tau).log()
+
+
+def sigmoid(X: Tensor, log: bool = False, fat: bool = False) -> Tensor:
+    """(log-)sigmoid with an optional fat tail (reference :493-507)."""
+    Y = log_fatmoid(X) if fat else logexpit(X)
+    return Y if log else Y.exp()
