@@ -3,5 +3,6 @@ from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement  # noqa
 from .monte_carlo import MCAcquisitionFunction, SampleReducingMCAcquisitionFunction  # noqa: F401
 from .objective import (GenericMCObjective, IdentityMCObjective, LinearMCObjective, MCAcquisitionObjective,  # noqa: F401
                         PosteriorTransform)
-from .mc_improvement import (qExpectedImprovement, qNoisyExpectedImprovement, qProbabilityOfImprovement,  # noqa: F401
-                             qSimpleRegret)
+from .mc_improvement import (qExpectedImprovement, qLowerConfidenceBound, qNoisyExpectedImprovement,  # noqa: F401
+                             qPosteriorStandardDeviation, qProbabilityOfImprovement, qSimpleRegret,
+                             qUpperConfidenceBound)

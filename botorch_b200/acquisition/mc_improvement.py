@@ -6,12 +6,14 @@ modes of `csrc/sample_reduce.cu`; everything upstream (covariance, contraction, 
 shared.  Anything the fused kernel does not cover falls back to the generic torch-op route."""
 from __future__ import annotations
 
+import math
 from functools import partial
 
 import torch
 from torch import Tensor
 
 from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement
+from .monte_carlo import SampleReducingMCAcquisitionFunction
 
 
 def _use_plain_reductions(acqf) -> None:
@@ -87,3 +89,42 @@ class qNoisyExpectedImprovement(qLogNoisyExpectedImprovement):
 
     def _sample_forward(self, obj: Tensor) -> Tensor:
         return (obj - self.compute_best_f(obj).unsqueeze(-1)).clamp_min(0)
+
+
+# ---- utilities whose per-sample value depends on the MC mean over ALL samples (no fused mode yet: generic route) ----------
+class qUpperConfidenceBound(SampleReducingMCAcquisitionFunction):
+    """MC-based batch UCB: mean_S max_q (mu + sqrt(beta pi / 2) |y - mu|), mu = MC mean (reference :833-906).  The
+    posterior comes from the CUDA kernels; the utility and reductions are torch ops on the materialised samples."""
+
+    def __init__(self, model, beta: float, sampler=None, objective=None, posterior_transform=None, X_pending=None) -> None:
+        super().__init__(model=model, sampler=sampler, objective=objective, posterior_transform=posterior_transform,
+                         X_pending=X_pending)
+        self.beta_prime = self._get_beta_prime(beta=beta)
+
+    def _get_beta_prime(self, beta: float) -> float:
+        return math.sqrt(beta * math.pi / 2)
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        mean = obj.mean(dim=0)
+        return mean + self.beta_prime * (obj - mean).abs()
+
+
+class qLowerConfidenceBound(qUpperConfidenceBound):
+    """Pessimistic counterpart of qUCB (reference :909-921)."""
+
+    def _get_beta_prime(self, beta: float) -> float:
+        return -super()._get_beta_prime(beta=beta)
+
+
+class qPosteriorStandardDeviation(SampleReducingMCAcquisitionFunction):
+    """MC-based batch posterior standard deviation: mean_S max_q sqrt(pi / 2) |y - mu| (reference :924-989)."""
+
+    def __init__(self, model, sampler=None, objective=None, posterior_transform=None, X_pending=None, constraints=None,
+                 eta=1e-3) -> None:
+        super().__init__(model=model, sampler=sampler, objective=objective, posterior_transform=posterior_transform,
+                         X_pending=X_pending, constraints=constraints, eta=eta)
+        self._scale = math.sqrt(math.pi / 2)
+
+    def _sample_forward(self, obj: Tensor) -> Tensor:
+        mean = obj.mean(dim=0)
+        return (obj - mean).abs() * self._scale

@@ -90,7 +90,8 @@ class SampleReducingMCAcquisitionFunction(MCAcquisitionFunction):
 def __getattr__(name: str):
     """qExpectedImprovement & co. live in `mc_improvement` (they build on the fused classes of `logei`, which imports
     this module); expose them under the reference's module path lazily."""
-    if name in ("qExpectedImprovement", "qNoisyExpectedImprovement", "qProbabilityOfImprovement", "qSimpleRegret"):
+    if name in ("qExpectedImprovement", "qNoisyExpectedImprovement", "qProbabilityOfImprovement", "qSimpleRegret",
+                "qUpperConfidenceBound", "qLowerConfidenceBound", "qPosteriorStandardDeviation"):
         from . import mc_improvement
 
         return getattr(mc_improvement, name)

@@ -145,3 +145,21 @@ def oracle_qnei(orc: OracleQLogNEI, X: Tensor) -> Tensor:
     obj = orc._f_X_samples(X).squeeze(-1)
     best = orc.baseline_best_f.view(orc.S, *([1] * (obj.dim() - 1)))
     return (obj - best).clamp_min(0).amax(dim=-1).mean(dim=0)
+
+
+def oracle_qucb(orc: OracleQLogEI, X: Tensor, beta: float, lower: bool = False) -> Tensor:
+    """qUpperConfidenceBound / qLowerConfidenceBound (monte_carlo.py:833-921): mean + (-)sqrt(beta pi / 2) |obj - mean|."""
+    import math
+
+    obj = orc.samples(X if X.dim() > 2 else X.unsqueeze(0)).squeeze(-1)
+    bp = math.sqrt(beta * math.pi / 2) * (-1.0 if lower else 1.0)
+    mean = obj.mean(dim=0)
+    return (mean + bp * (obj - mean).abs()).amax(dim=-1).mean(dim=0)
+
+
+def oracle_qpstd(orc: OracleQLogEI, X: Tensor) -> Tensor:
+    """qPosteriorStandardDeviation (monte_carlo.py:924-989)."""
+    import math
+
+    obj = orc.samples(X if X.dim() > 2 else X.unsqueeze(0)).squeeze(-1)
+    return ((obj - obj.mean(dim=0)).abs() * math.sqrt(math.pi / 2)).amax(dim=-1).mean(dim=0)

@@ -69,3 +69,16 @@ def test_qnei_matches_oracle_and_generic_route():
     assert float(vb.detach().abs().max()) > 0
     assert float((va - vb).detach().abs().max() / vb.detach().abs().max()) < 1e-9
     assert float((ga - gb).abs().max() / gb.abs().max()) < 1e-7
+
+
+def test_qucb_qlcb_qpstd_match_oracle():
+    """Utilities that depend on the MC mean over all samples: generic route on CUDA posteriors against the oracle."""
+    from botorch_b200.acquisition import qLowerConfidenceBound, qPosteriorStandardDeviation, qUpperConfidenceBound
+    from botorch_b200.sampling import SobolQMCNormalSampler
+    from oracle import acquisition as oa
+
+    data, model, orc, X, dev = _setup("C1", S=256)
+    mk = lambda: SobolQMCNormalSampler(torch.Size([256]), seed=1234)
+    _check(qUpperConfidenceBound(model, beta=2.0, sampler=mk()), lambda x: oa.oracle_qucb(orc, x, 2.0), X, dev)
+    _check(qLowerConfidenceBound(model, beta=2.0, sampler=mk()), lambda x: oa.oracle_qucb(orc, x, 2.0, lower=True), X, dev)
+    _check(qPosteriorStandardDeviation(model, sampler=mk()), lambda x: oa.oracle_qpstd(orc, x), X, dev)
