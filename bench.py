@@ -202,6 +202,8 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    pts_local_scale = b_total * spec.q * spec.S  # whole-job points per step (every rank sweeps its shard concurrently)
+
     def measure(mode: str, with_clocks: bool):
         """Build the model in the given contraction mode and time K resident steps and K host-buffer (e2e) steps."""
         with settings.contraction(mode):
@@ -243,7 +245,33 @@ def main():
             for _ in range(2):
                 step_e2e()
             ms_e2e = timed(step_e2e, args.steps)
-        return {"model": model, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "clocks": clock_info}
+            phases = None
+            if with_clocks:
+                # the other two shapes SURVEY.md section 8(d) asks for: the raw-sample sweep without gradient, and one
+                # L-BFGS round (b = num_restarts q-batches, forward + backward, a latency-bound call)
+                def step_fwd():
+                    with torch.no_grad():
+                        for i in range(0, b_local, chunk):
+                            acqf(X_dev[i:i + chunk])
+
+                step_fwd()
+                ms_fwd = timed(step_fwd, args.steps)
+                nr = max(1, min(spec.num_restarts, b_local))
+
+                def step_round():
+                    Xc = X_dev[:nr].detach().requires_grad_(True)
+                    v = acqf(Xc)
+                    torch.autograd.grad(v.sum(), Xc)
+
+                for _ in range(3):
+                    step_round()
+                ms_round = timed(step_round, 20) / 20
+                phases = {"sweep_forward_only_points_per_s": pts_local_scale * args.steps / (ms_fwd * 1e-3),
+                          "sweep_forward_only_ms_per_step": ms_fwd / args.steps,
+                          "lbfgs_round": {"q_batches": nr, "ms_per_fwd_bwd_call": ms_round,
+                                          "note": "per rank, not sharded: one optimiser round over num_restarts q-batches"}}
+        return {"model": model, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "clocks": clock_info,
+                "phases": phases}
 
     other = "dmma" if args.contraction == "int8" else "int8"
     head = measure(args.contraction, with_clocks=True)
@@ -364,7 +392,7 @@ def main():
                                            else "dmma: FP64 DMMA tensor-core kernel")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
                         "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "phases": head["phases"],
                 "alt_mode": {"contraction": other, "value": pts_per_step * args.steps / (alt["ms_total"] * 1e-3),
                              "ms_per_step": alt["ms_total"] / args.steps,
                              "e2e_value": pts_per_step * args.steps / (alt["ms_e2e"] * 1e-3), "roofline": roofline_alt}}

@@ -57,6 +57,11 @@ __device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uin
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void oz_tma_3d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void oz_tma_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
                ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
@@ -97,11 +102,12 @@ struct OzTile { int64_t mt; int nt; int kb0, kb1; };
 // returns false past the end.  The k-range is the union over the cluster's column tiles (the extra k-blocks of the
 // narrower columns multiply stored zeros of the triangular factor).
 template <int OZ_BK, int OZ_BN, int CM, int CN>
-__device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, OzTile& o) {
+__device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles, int k_blocks, int tri_mode, int group_m,
+                                        OzTile& o) {
   const int64_t cm_tiles = (m_tiles + CM - 1) / CM;
   const int cn_tiles = (n_tiles + CN - 1) / CN;
   if (t >= cm_tiles * cn_tiles) return false;
-  constexpr int GM = (OZ_GROUP_M / CM) > 0 ? (OZ_GROUP_M / CM) : 1;
+  const int GM = (group_m / CM) > 0 ? (group_m / CM) : 1;
   const int64_t group_sz = (int64_t)GM * cn_tiles;
   const int64_t grp = t / group_sz;
   const int64_t m0 = grp * GM;
@@ -120,7 +126,7 @@ template <int OZ_BK, int OZ_BN, int CM, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
                   int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
-                  const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc) {
+                  const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc, int l2_hints, int group_m) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
@@ -166,14 +172,22 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // ================= TMA producer =================
       int64_t it = 0;  // k-block counter across tiles
       OzTile tl;
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters) {
+      uint64_t pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters) {
         const int row0 = (int)((tl.mt * CM + rm) * OZ_BM), col0 = (tl.nt * CN + rn) * OZ_BN;
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
           const int s = (int)(it % stages);
           if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
           oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + (size_t)s * stage_bytes;
-          if (CSIZE == 1) {
+          if (CSIZE == 1 && l2_hints) {
+            // the B slices (the triangular factor, re-used by every row tile of the launch) are kept in L2 with
+            // evict_last; the A slices are only re-used by the column tiles of the current row group
+            for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
+            for (int q = 0; q < G; q++)
+              oz_tma_3d_hint(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, pol_keep);
+          } else if (CSIZE == 1) {
             for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
             for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
           } else {
@@ -191,7 +205,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       int64_t it = 0, tile_i = 0;
       OzTile tl;
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
         if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
           oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -231,7 +245,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int etid = tid - 64;                // 0..127
     int64_t tile_i = 0;
     OzTile tl;
-    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, tl); t += num_clusters, tile_i++) {
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
       const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
       const int col0 = (tl.nt * CN + rn) * OZ_BN;
       // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
@@ -290,9 +304,11 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (row_ok && col0 + c0 < N) {
           if (col0 + c0 + 16 <= N && vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2)
-              *reinterpret_cast<double2*>(dst + c0 + j) =
-                  make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+            for (int j = 0; j < 16; j += 2) {
+              const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+              if (l2_hints) __stcs(reinterpret_cast<double2*>(dst + c0 + j), o);  // streamed: consumed by a later kernel
+              else *reinterpret_cast<double2*>(dst + c0 + j) = o;
+            }
           } else {
             for (int j = 0; j < 16; j++) if (col0 + c0 + j < N) dst[c0 + j] = acc[j] * rs * s_col[c0 + j];
           }
@@ -424,12 +440,14 @@ static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri
       max_clusters = sms;
     }
   }
+  const int l2_hints = (getenv("MCACQ_OZ_HINT") != nullptr) ? atoi(getenv("MCACQ_OZ_HINT")) : 1;
+  const int group_m = (getenv("MCACQ_OZ_GROUP") != nullptr) ? atoi(getenv("MCACQ_OZ_GROUP")) : OZ_GROUP_M;
   const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
   const int64_t n_tiles = (N + OZ_BN - 1) / OZ_BN;
   const int64_t ctiles = ((m_tiles + CM - 1) / CM) * ((n_tiles + CN - 1) / CN);
   const int nclusters = (int)(ctiles < max_clusters ? ctiles : max_clusters);
   cfg.gridDim = dim3(nclusters * CS);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc, l2_hints, group_m);
   count_launch();
   if (e != cudaSuccess) return (int)e;
   MCACQ_CUDA_CHECK_LAUNCH();
