@@ -20,6 +20,9 @@ namespace mcacq {
 // defined in blocks.cu / sample_reduce.cu / cov.cu
 int unscale_grad(const double* dU, int64_t rows, int d, const double* coef, const double* ls, double* dX, cudaStream_t st);
 int fill_value(double* p, int64_t n, double v, cudaStream_t st);
+int cov_cross_bwd_split(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2, int d,
+                        double* W, int64_t ldw, const double* row_scale, const double* col_vec, double* dU1, int accumulate,
+                        cudaStream_t st);
 
 }  // namespace mcacq
 
@@ -197,7 +200,7 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   } else {
     if ((rc = mcacq_dgemm_tri(MCACQ_TRI_LOWER, M, model->np, w.A, model->Rt, w.Kt, w.counter, st))) return rc;
   }
-  if ((rc = mcacq_cov_cross_bwd(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
+  if ((rc = cov_cross_bwd_split(model->kernel_id, model->outputscale, w.U, M, model->U_train, model->n, model->d, w.Kt,
                                 model->np, w.row_scale, model->alpha, w.dU, /*accumulate=*/1, st)))
     return rc;
   return unscale_grad(w.dU, M, model->d, model->x_coef, model->lengthscale, grad_X, st);

@@ -50,15 +50,34 @@ __device__ __forceinline__ void loadn(const double* p, bool ok, double (&v)[N]) 
 }
 
 constexpr int BLK_WARPS = 4;
+constexpr int BWD_CHUNK = 512;  // output columns per warp of the backward kernel (a multiple of its 32-column step)
 
+// Number of k-slices (= warps per CTA) of the forward kernel: as many as keep the cross-warp reduction buffer <= 48 KB.
+template <int QT, int RT, int NB>
+struct FwdSplit {
+  static constexpr int NACC = 2 * QT * QT + 2 * QT * RT + 2 * QT;  // Gram + cross-Gram fragments + mean + row max, per lane
+  static constexpr int KS = (8 * NB * NACC * 256 <= 49152) ? 8 : (4 * NB * NACC * 256 <= 49152) ? 4
+                          : (2 * NB * NACC * 256 <= 49152) ? 2 : 1;
+};
+
+// One CTA owns NB consecutive q-batches; its KS warps split the contraction dimension into KS contiguous slices, sweep them
+// concurrently (an L-BFGS round of ~64 q-batches still occupies hundreds of warps) and combine the partial DMMA
+// fragments through shared memory in slice order.  The decomposition depends on np only, never on b, so the results are
+// bit-identical however a t-batch is chunked.
 template <int QT, int RT, int NB, bool MEAN>
-__global__ void __launch_bounds__(BLK_WARPS * 32)
+__global__ void __launch_bounds__(FwdSplit<QT, RT, NB>::KS * 32)
 posterior_blocks_kernel(BlocksParams p) {
+  constexpr int KS = FwdSplit<QT, RT, NB>::KS;
+  constexpr int NACC = FwdSplit<QT, RT, NB>::NACC;
+  extern __shared__ __align__(16) double red[];   // [KS][NB][NACC][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int64_t b0 = ((int64_t)blockIdx.x * BLK_WARPS + warp) * NB;
+  const int64_t b0 = (int64_t)blockIdx.x * NB;
   if (b0 >= p.b) return;
   const int q = p.q, np = p.np, r = p.r;
+  const int kslice = ((np / 16 + KS - 1) / KS) * 16;             // columns per warp (a multiple of the 16-column step)
+  const int k_begin = warp * kslice;
+  const int k_end = (k_begin + kslice < np) ? k_begin + kslice : np;
 
   double accG[NB][QT][QT][2];
   double accB[NB][QT][RT > 0 ? RT : 1][2];
@@ -85,20 +104,22 @@ posterior_blocks_kernel(BlocksParams p) {
   double al[4] = {0.0, 0.0, 0.0, 0.0};
   const int64_t off0 = (b0 * q + g) * (int64_t)np + 4 * t4;   // fragment (nb, mi) starts at off0 + (nb * q + 8 * mi) * np
   const int64_t bstride = (int64_t)q * np;
+  const bool live = k_begin < k_end;
 #pragma unroll
   for (int nb = 0; nb < NB; nb++)
 #pragma unroll
     for (int mi = 0; mi < QT; mi++) {
-      const bool ok = (b0 + nb < p.b) && mi * 8 + g < q;
-      load4(p.A + off0 + nb * bstride + (int64_t)mi * 8 * np, ok, af[nb][mi]);
-      if (MEAN) load4(p.Kt + off0 + nb * bstride + (int64_t)mi * 8 * np, ok, kf[nb][mi]);
+      const bool ok = live && (b0 + nb < p.b) && mi * 8 + g < q;
+      load4(p.A + off0 + nb * bstride + (int64_t)mi * 8 * np + k_begin, ok, af[nb][mi]);
+      if (MEAN) load4(p.Kt + off0 + nb * bstride + (int64_t)mi * 8 * np + k_begin, ok, kf[nb][mi]);
     }
 #pragma unroll
-  for (int nj = 0; nj < RT; nj++) load4(p.A_base + (int64_t)(nj * 8 + g) * np + 4 * t4, nj * 8 + g < r, bf[nj]);
-  if (MEAN) load4(p.alpha + 4 * t4, true, al);
+  for (int nj = 0; nj < RT; nj++)
+    load4(p.A_base + (int64_t)(nj * 8 + g) * np + k_begin + 4 * t4, live && nj * 8 + g < r, bf[nj]);
+  if (MEAN && live) load4(p.alpha + k_begin + 4 * t4, true, al);
 
-  for (int k0 = 0; k0 < np; k0 += 16) {
-    const bool more = k0 + 16 < np;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+    const bool more = k0 + 16 < k_end;
 #pragma unroll
     for (int nb = 0; nb < NB; nb++) {
 #pragma unroll
@@ -134,24 +155,74 @@ posterior_blocks_kernel(BlocksParams p) {
     if (MEAN) load4(p.alpha + k0 + 16 + 4 * t4, more, al);
   }
 
-  const double s2 = p.y_std * p.y_std;
+  // ---- combine the KS partial results (slice order) -- warp nb finishes q-batch b0 + nb
+  if (KS > 1) {
 #pragma unroll
-  for (int nb = 0; nb < NB; nb++) {
+    for (int nb = 0; nb < NB; nb++) {
+      double* dst = red + ((size_t)(warp * NB + nb) * NACC) * 32 + lane;
+      int a = 0;
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+#pragma unroll
+        for (int nj = 0; nj < QT; nj++) { dst[32 * a++] = accG[nb][mi][nj][0]; dst[32 * a++] = accG[nb][mi][nj][1]; }
+#pragma unroll
+        for (int nj = 0; nj < RT; nj++) { dst[32 * a++] = accB[nb][mi][nj][0]; dst[32 * a++] = accB[nb][mi][nj][1]; }
+        dst[32 * a++] = macc[nb][mi];
+        dst[32 * a++] = amax[nb][mi];
+      }
+    }
+    __syncthreads();
+  }
+  const double s2 = p.y_std * p.y_std;
+  for (int nb = (KS > 1 ? warp : 0); nb < NB; nb += (KS > 1 ? KS : 1)) {
     const int64_t bb = b0 + nb;
     if (bb >= p.b) continue;
+    double G_[QT][QT][2], B_[QT][RT > 0 ? RT : 1][2], mv_[QT], av_[QT];
+    if (KS > 1) {
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        mv_[mi] = 0.0; av_[mi] = 0.0;
+#pragma unroll
+        for (int nj = 0; nj < QT; nj++) { G_[mi][nj][0] = 0.0; G_[mi][nj][1] = 0.0; }
+#pragma unroll
+        for (int nj = 0; nj < (RT > 0 ? RT : 1); nj++) { B_[mi][nj][0] = 0.0; B_[mi][nj][1] = 0.0; }
+      }
+      for (int w = 0; w < KS; w++) {
+        const double* src = red + ((size_t)(w * NB + nb) * NACC) * 32 + lane;
+        int a = 0;
+#pragma unroll
+        for (int mi = 0; mi < QT; mi++) {
+#pragma unroll
+          for (int nj = 0; nj < QT; nj++) { G_[mi][nj][0] += src[32 * a++]; G_[mi][nj][1] += src[32 * a++]; }
+#pragma unroll
+          for (int nj = 0; nj < RT; nj++) { B_[mi][nj][0] += src[32 * a++]; B_[mi][nj][1] += src[32 * a++]; }
+          mv_[mi] += src[32 * a++];
+          av_[mi] = fmax(av_[mi], src[32 * a++]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        mv_[mi] = macc[nb][mi]; av_[mi] = amax[nb][mi];
+#pragma unroll
+        for (int nj = 0; nj < QT; nj++) { G_[mi][nj][0] = accG[nb][mi][nj][0]; G_[mi][nj][1] = accG[nb][mi][nj][1]; }
+#pragma unroll
+        for (int nj = 0; nj < RT; nj++) { B_[mi][nj][0] = accB[nb][mi][nj][0]; B_[mi][nj][1] = accB[nb][mi][nj][1]; }
+      }
+    }
     const double* Ub = p.U + bb * q * p.d;
 #pragma unroll
     for (int mi = 0; mi < QT; mi++) {
       // mean: reduce the 4 lanes of a row group
-      double mv = macc[nb][mi];
+      double mv = mv_[mi];
       mv += __shfl_xor_sync(0xffffffffu, mv, 1);
       mv += __shfl_xor_sync(0xffffffffu, mv, 2);
-      double av = amax[nb][mi];
+      double av = av_[mi];
       av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 1));
       av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 2));
       const int i = mi * 8 + g;
       if (t4 == 0 && i < q) {
-        if (p.mean_part != nullptr) {  // int8 mode: Kt * alpha was reduced per 64-column tile by the covariance kernel
+        if (p.mean_part != nullptr) {  // int8 mode: Kt * alpha was reduced per 512-column tile by the covariance kernel
           const int64_t Mrows = p.b * q;
           mv = 0.0;
           for (int t = 0; t < p.n_parts; t++) mv += p.mean_part[(int64_t)t * Mrows + bb * q + i];
@@ -171,7 +242,7 @@ posterior_blocks_kernel(BlocksParams p) {
             double df = Ub[i * p.d + k] - Ub[j * p.d + k];
             sq = fma(df, df, sq);
           }
-          double v = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - accG[nb][mi][nj][e]);
+          double v = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - G_[mi][nj][e]);
           p.Sxx[(bb * q + i) * q + j] = v;
           if (nj < mi) p.Sxx[(bb * q + j) * q + i] = v;
         }
@@ -186,7 +257,7 @@ posterior_blocks_kernel(BlocksParams p) {
             double df = Ub[i * p.d + k] - p.U_base[j * p.d + k];
             sq = fma(df, df, sq);
           }
-          p.Sxb[(bb * q + i) * r + j] = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - accB[nb][mi][nj][e]);
+          p.Sxb[(bb * q + i) * r + j] = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - B_[mi][nj][e]);
         }
     }
   }
@@ -199,12 +270,18 @@ posterior_blocks_kernel(BlocksParams p) {
 
 template <int QT, int RT>
 __global__ void __launch_bounds__(BLK_WARPS * 32)
-posterior_blocks_bwd_kernel(BlocksBwdParams p) {
+posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int64_t bb = (int64_t)blockIdx.x * BLK_WARPS + warp;
+  // one warp per (q-batch, chunk of BWD_CHUNK output columns): the columns are independent, so splitting them keeps
+  // every result bit-identical while an L-BFGS round (b = num_restarts ~ 64 q-batches) still fills the machine
+  const int n_chunks = (p.np + col_chunk - 1) / col_chunk;
+  const int64_t wid = (int64_t)blockIdx.x * BLK_WARPS + warp;
+  const int64_t bb = wid / n_chunks;
+  const int chunk = (int)(wid - bb * n_chunks);
   if (bb >= p.b) return;
   const int q = p.q, np = p.np, r = p.r, d = p.d;
+  const int col_begin = chunk * col_chunk, col_end = (col_begin + col_chunk < np) ? col_begin + col_chunk : np;
   const double s2 = p.y_std * p.y_std;
   const double* gxx = p.gSxx + bb * q * q;
   const double* gxb = p.gSxb + bb * q * r;
@@ -249,7 +326,7 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
       if (bnd > 0.0 && isfinite(bnd)) frexp(bnd * (1.0 + 1e-9), &ex);
       shift[mi] = 8 * p.G - 2 - ex;
       const int i = mi * 8 + g;
-      if (t4 == 0 && i < q) p.slice_scale[bb * q + i] = ldexp(1.0, ex + 2);
+      if (t4 == 0 && i < q && chunk == 0) p.slice_scale[bb * q + i] = ldexp(1.0, ex + 2);
     }
   }
   const size_t slice_stride = (size_t)p.b * q * np;
@@ -264,11 +341,12 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
   double rq[2 * QT][NT];
   double rb[RT > 0 ? 2 * RT : 1][NT];
 #pragma unroll
-  for (int kk = 0; kk < 2 * QT; kk++) loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + NT * g, kk * 4 + t4 < q && NT * g < np, rq[kk]);
+  for (int kk = 0; kk < 2 * QT; kk++)
+    loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + col_begin + NT * g, kk * 4 + t4 < q && col_begin + NT * g < col_end, rq[kk]);
 #pragma unroll
   for (int kk = 0; kk < 2 * RT; kk++)
-    loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + NT * g, kk * 4 + t4 < r && NT * g < np, rb[kk]);
-  for (int c0 = 0; c0 < np; c0 += 8 * NT) {
+    loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + col_begin + NT * g, kk * 4 + t4 < r && col_begin + NT * g < col_end, rb[kk]);
+  for (int c0 = col_begin; c0 < col_end; c0 += 8 * NT) {
     const int cn = c0 + 8 * NT + NT * g;  // this lane's source columns in the next step
     double acc[QT][NT][2];
 #pragma unroll
@@ -281,7 +359,7 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
       for (int mi = 0; mi < QT; mi++)
 #pragma unroll
         for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cb[mi][kk], rb[kk][t]);
-      loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < r && cn < np, rb[kk]);
+      loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < r && cn < col_end, rb[kk]);
     }
 #pragma unroll
     for (int kk = 0; kk < 2 * QT; kk++) {
@@ -289,13 +367,13 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
       for (int mi = 0; mi < QT; mi++)
 #pragma unroll
         for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cq[mi][kk], rq[kk][t]);
-      loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < q && cn < np, rq[kk]);
+      loadn<NT>(Ab + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < q && cn < col_end, rq[kk]);
     }
     // every lane of the warp has issued its loads of this step's columns (they were fetched one step earlier) before
     // any lane overwrites them in place
     __syncwarp();
     const int oc = c0 + 2 * NT * t4;
-    if (oc < np) {
+    if (oc < col_end) {
 #pragma unroll
       for (int mi = 0; mi < QT; mi++) {
         const int i = mi * 8 + g;
@@ -330,7 +408,8 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
     }
   }
 
-  // rank-1 mean term scale and direct kernel terms
+  // rank-1 mean term scale and direct kernel terms (once per q-batch)
+  if (chunk != 0) return;
   const double* Ub = p.U + bb * q * d;
   for (int idx = lane; idx < q; idx += 32) p.row_scale[bb * q + idx] = p.y_std * p.gmean[bb * q + idx];
   for (int idx = lane; idx < q * d; idx += 32) {
@@ -361,11 +440,12 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p) {
 
 template <int QT, int RT>
 static int launch_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
-  constexpr int NB = (QT == 1 && RT <= 4) ? 4 : 1;
-  int64_t per_cta = (int64_t)BLK_WARPS * NB;
-  int64_t blocks = (p.b + per_cta - 1) / per_cta;
-  if (p.Kt != nullptr) posterior_blocks_kernel<QT, RT, NB, true><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
-  else posterior_blocks_kernel<QT, RT, NB, false><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  constexpr int NB = (QT == 1 && RT <= 4) ? 2 : 1;
+  constexpr int KS = FwdSplit<QT, RT, NB>::KS;
+  const size_t smem = (KS > 1) ? (size_t)KS * NB * FwdSplit<QT, RT, NB>::NACC * 32 * sizeof(double) : 0;
+  int64_t blocks = (p.b + NB - 1) / NB;
+  if (p.Kt != nullptr) posterior_blocks_kernel<QT, RT, NB, true><<<(unsigned)blocks, KS * 32, smem, st>>>(p);
+  else posterior_blocks_kernel<QT, RT, NB, false><<<(unsigned)blocks, KS * 32, smem, st>>>(p);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
@@ -373,8 +453,12 @@ static int launch_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
 
 template <int QT, int RT>
 static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
-  int64_t blocks = (p.b + BLK_WARPS - 1) / BLK_WARPS;
-  posterior_blocks_bwd_kernel<QT, RT><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p);
+  // the output columns are independent, so the chunk width is free to follow the batch size: one warp per q-batch when
+  // there are thousands of them (no duplicated preamble), 512-column chunks when an L-BFGS round brings only a few dozen
+  const int col_chunk = (p.b >= 2048) ? ((p.np + 31) / 32) * 32 : BWD_CHUNK;
+  const int64_t warps = p.b * ((p.np + col_chunk - 1) / col_chunk);
+  int64_t blocks = (warps + BLK_WARPS - 1) / BLK_WARPS;
+  posterior_blocks_bwd_kernel<QT, RT><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

@@ -154,6 +154,7 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
 //   the extra all-ones column yields the row sums for free.
 constexpr int BW_T = 64;        // rows per CTA and columns per tile
 constexpr int BW_P = BW_T + 4;  // padded pitch: conflict-free 8x4 / 4x8 fragment reads
+constexpr int BW_CHUNK = 512;   // columns per CTA in split mode (a multiple of BW_T, >= MCACQ_MAX_D)
 
 __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -166,7 +167,11 @@ __global__ void __launch_bounds__(256, 2)
 cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict__ U1, int64_t m1,
                      const double* __restrict__ U2, int m2, int d, const double* __restrict__ W, int64_t ldw,
                      const double* __restrict__ row_scale, const double* __restrict__ col_vec,
-                     double* __restrict__ dU1, int accumulate) {
+                     double* __restrict__ dU1, int accumulate, int col_chunk, double* __restrict__ parts) {
+  // col_chunk > 0 (split mode): blockIdx.y owns the columns [y * col_chunk, (y + 1) * col_chunk) -- the last chunk also
+  // takes the remainder -- and leaves its PARTIAL result in the first d columns of its own (now dead) block of W
+  // (`parts` == W); `reduce_col_parts_kernel` then adds the chunks in ascending order.  The decomposition depends on m2
+  // only, never on the number of rows, so results stay bit-identical however a t-batch is chunked.
   constexpr int DP = 8 * NTD;
   extern __shared__ __align__(16) double sm[];
   double* s1 = sm;                         // [d][BW_T]      U1^T tile (rows of this CTA)
@@ -195,16 +200,19 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
 #pragma unroll
   for (int j = 0; j < NTD; j++) { vacc[j][0] = 0.0; vacc[j][1] = 0.0; }
 
-  for (int c0 = 0; c0 < m2; c0 += BW_T) {
+  const int n_chunks = (col_chunk > 0) ? (int)gridDim.y : 1;
+  const int col_begin = (col_chunk > 0) ? (int)blockIdx.y * col_chunk : 0;
+  const int col_end = (col_chunk > 0 && (int)blockIdx.y + 1 < n_chunks) ? col_begin + col_chunk : m2;
+  for (int c0 = col_begin; c0 < col_end; c0 += BW_T) {
     __syncthreads();  // previous tile's DMMA reads of s2 / sG are done
     for (int idx = tid; idx < BW_T * d; idx += 256) {
       int p = idx / d, k = idx - p * d;
       int gc = c0 + p;
-      s2[k * BW_P + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
+      s2[k * BW_P + p] = (gc < col_end) ? U2[(int64_t)gc * d + k] : 0.0;
     }
     for (int p = tid; p < BW_T; p += 256) {
       int gc = c0 + p;
-      sc[p] = (col_vec != nullptr && gc < m2) ? col_vec[gc] : 0.0;
+      sc[p] = (col_vec != nullptr && gc < col_end) ? col_vec[gc] : 0.0;
     }
     // the 4 x 4 block of upstream gradients W is requested before the barrier and the distance loop so that its HBM
     // latency is covered by them
@@ -217,13 +225,13 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
       for (int j = 0; j < 4; j++) w[i][j] = 0.0;
       if (gr < m1) {
         const double* wp = W + gr * ldw + gc0;
-        if (gc0 + 3 < m2 && ((ldw & 1) == 0)) {
+        if (gc0 + 3 < col_end && ((ldw & 1) == 0)) {
           double2 w01 = *reinterpret_cast<const double2*>(wp);
           double2 w23 = *reinterpret_cast<const double2*>(wp + 2);
           w[i][0] = w01.x; w[i][1] = w01.y; w[i][2] = w23.x; w[i][3] = w23.y;
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; j++) if (gc0 + j < m2) w[i][j] = wp[j];
+          for (int j = 0; j < 4; j++) if (gc0 + j < col_end) w[i][j] = wp[j];
         }
       }
     }
@@ -255,7 +263,7 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
       double gv[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const bool ok = (gr < m1) && (gc0 + j < m2);
+        const bool ok = (gr < m1) && (gc0 + j < col_end);
         gv[j] = ok ? (w[i][j] + rs * sc[tx * 4 + j]) * kernel_dfactor(kernel_id, outputscale, sq[i][j]) : 0.0;
       }
       *reinterpret_cast<double4*>(sG + (ty * 4 + i) * BW_P + tx * 4) = make_double4(gv[0], gv[1], gv[2], gv[3]);
@@ -285,8 +293,12 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
     int64_t gr = row0 + p;
     if (gr < m1) {
       double v = s1[k * BW_T + p] * sV[p * DP + d] - sV[p * DP + k];
-      double* dst = dU1 + gr * d + k;
-      *dst = accumulate ? (*dst + v) : v;
+      if (col_chunk > 0) {
+        parts[gr * ldw + col_begin + k] = v;
+      } else {
+        double* dst = dU1 + gr * d + k;
+        *dst = accumulate ? (*dst + v) : v;
+      }
     }
   }
 }
@@ -386,20 +398,68 @@ extern "C" int mcacq_cov_cross_sliced(int kernel_id, double outputscale, const d
 }
 
 namespace mcacq {
+__global__ void reduce_col_parts_kernel(const double* __restrict__ parts, int64_t ldw, int n_chunks, int col_chunk,
+                                        int64_t m1, int d, double* __restrict__ dU1, int accumulate) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= m1 * d) return;
+  const int64_t row = idx / d;
+  const int k = (int)(idx - row * d);
+  double v = accumulate ? dU1[idx] : 0.0;
+  for (int c = 0; c < n_chunks; c++) v += parts[row * ldw + (int64_t)c * col_chunk + k];
+  dU1[idx] = v;
+}
+
 template <int NTD>
 static int launch_cov_bwd(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
                           int d, const double* W, int64_t ldw, const double* row_scale, const double* col_vec,
-                          double* dU1, int accumulate, cudaStream_t st) {
+                          double* dU1, int accumulate, double* parts, cudaStream_t st) {
   constexpr int DP = 8 * NTD;
   size_t smem = ((size_t)d * BW_T + (size_t)DP * BW_P + (size_t)BW_T * BW_P + 2 * BW_T) * sizeof(double);
   auto kern = cov_cross_bwd_kernel<NTD>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t blocks = (m1 + BW_T - 1) / BW_T;
+  const int n_chunks = (parts != nullptr) ? m2 / BW_CHUNK : 1;   // every chunk >= BW_CHUNK >= d columns wide
+  if (n_chunks >= 2) {
+    kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), 256, smem, st>>>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw,
+                                                                         row_scale, col_vec, dU1, accumulate, BW_CHUNK, parts);
+    count_launch();
+    MCACQ_CUDA_CHECK_LAUNCH();
+    const int64_t total = m1 * d;
+    reduce_col_parts_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(parts, ldw, n_chunks, BW_CHUNK, m1, d, dU1,
+                                                                              accumulate);
+    count_launch();
+    MCACQ_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   kern<<<(unsigned)blocks, 256, smem, st>>>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1,
-                                            accumulate);
+                                            accumulate, 0, nullptr);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+static int cov_cross_bwd_dispatch(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
+                                  int d, const double* W, int64_t ldw, const double* row_scale, const double* col_vec,
+                                  double* dU1, int accumulate, double* parts, cudaStream_t st) {
+#define MCACQ_BWD_CASE(NT) \
+  return launch_cov_bwd<NT>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate, parts, st)
+  const int ntd = (d + 1 + 7) / 8;  // 8 * NTD >= d + 1 (one extra all-ones column for the row sums)
+  if (ntd <= 1) MCACQ_BWD_CASE(1);
+  if (ntd <= 2) MCACQ_BWD_CASE(2);
+  if (ntd <= 3) MCACQ_BWD_CASE(3);
+  if (ntd <= 4) MCACQ_BWD_CASE(4);
+  if (ntd <= 6) MCACQ_BWD_CASE(6);
+  MCACQ_BWD_CASE(9);
+#undef MCACQ_BWD_CASE
+}
+
+// Fused-path variant: W is workspace that dies with this call, so the column chunks may park their partial results in it
+// (see cov_cross_bwd_kernel); many more CTAs than row tiles, which is what an L-BFGS round (a few hundred rows) needs.
+int cov_cross_bwd_split(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2, int d,
+                        double* W, int64_t ldw, const double* row_scale, const double* col_vec, double* dU1, int accumulate,
+                        cudaStream_t st) {
+  if (m1 == 0) return 0;
+  return cov_cross_bwd_dispatch(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate, W, st);
 }
 }  // namespace mcacq
 
@@ -411,14 +471,7 @@ extern "C" int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const doub
   if (d > MCACQ_MAX_D) return MCACQ_ELIMIT;
   if (m1 == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define MCACQ_BWD_CASE(NT) \
-  return launch_cov_bwd<NT>(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate, st)
-  const int ntd = (d + 1 + 7) / 8;  // 8 * NTD >= d + 1 (one extra all-ones column for the row sums)
-  if (ntd <= 1) MCACQ_BWD_CASE(1);
-  if (ntd <= 2) MCACQ_BWD_CASE(2);
-  if (ntd <= 3) MCACQ_BWD_CASE(3);
-  if (ntd <= 4) MCACQ_BWD_CASE(4);
-  if (ntd <= 6) MCACQ_BWD_CASE(6);
-  MCACQ_BWD_CASE(9);
-#undef MCACQ_BWD_CASE
+  return cov_cross_bwd_dispatch(kernel_id, outputscale, U1, m1, U2, m2, d, W, ldw, row_scale, col_vec, dU1, accumulate,
+                                /*parts=*/nullptr, st);
 }
+
