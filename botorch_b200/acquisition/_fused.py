@@ -71,7 +71,7 @@ class LaunchStats:
 def _raise_on_info(info: Tensor) -> None:
     """Mirror the reference's numerical signalling: NumericalWarning on jitter (psd_safe_cholesky),
     NotPSDError after 6 tries, NanError on non-finite samples (utils/low_rank.py:162-171)."""
-    flags = int(torch.bitwise_or(info, torch.zeros_like(info)).max().item()) if info.numel() else 0
+    flags = int(info.max().item()) if info.numel() else 0  # all status words are non-negative bit sets: max == 0 <=> all clear
     if flags == 0:
         return
     host = info.cpu()

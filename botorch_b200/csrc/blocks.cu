@@ -50,7 +50,6 @@ __device__ __forceinline__ void loadn(const double* p, bool ok, double (&v)[N]) 
 }
 
 constexpr int BLK_WARPS = 4;
-constexpr int BWD_CHUNK = 512;  // output columns per warp of the backward kernel (a multiple of its 32-column step)
 
 // Number of k-slices (= warps per CTA) of the forward kernel: as many as keep the cross-warp reduction buffer <= 48 KB.
 template <int QT, int RT, int NB>
@@ -454,8 +453,12 @@ static int launch_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
 template <int QT, int RT>
 static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
   // the output columns are independent, so the chunk width is free to follow the batch size: one warp per q-batch when
-  // there are thousands of them (no duplicated preamble), 512-column chunks when an L-BFGS round brings only a few dozen
-  const int col_chunk = (p.b >= 2048) ? ((p.np + 31) / 32) * 32 : BWD_CHUNK;
+  // there are thousands of them (no duplicated preamble), narrow chunks when an L-BFGS round brings only a few dozen
+  int col_chunk = ((p.np + 31) / 32) * 32;
+  if (p.b < 2048) {  // aim at >= 2048 warps, at least 4 steps of 32 columns each
+    int64_t c = ((p.b * (int64_t)p.np / 2048) / 32) * 32;
+    col_chunk = (int)(c < 128 ? 128 : (c > col_chunk ? col_chunk : c));
+  }
   const int64_t warps = p.b * ((p.np + col_chunk - 1) / col_chunk);
   int64_t blocks = (warps + BLK_WARPS - 1) / BLK_WARPS;
   posterior_blocks_bwd_kernel<QT, RT><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);

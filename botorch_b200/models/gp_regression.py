@@ -125,13 +125,15 @@ class SingleTaskGP(Model):
 
     # ------------------------------------------------------------------ device caches
     def _hyper_key(self):
+        """Identity of the fitted state WITHOUT touching device memory: storage pointer + in-place version counter of every
+        hyper-parameter tensor (an optimiser round calls this twice; copying the values to the host would cost a
+        device synchronisation per hyper-parameter per call)."""
         base = self._base_kernel()
-        vals = [base.lengthscale.detach().reshape(-1), self.likelihood.noise.detach().reshape(-1),
-                self.mean_module.constant.detach().reshape(-1)]
+        tensors = [base.lengthscale, self.likelihood.noise, self.mean_module.constant, self.train_inputs[0], self.train_targets]
         if isinstance(self.covar_module, ScaleKernel):
-            vals.append(self.covar_module.outputscale.detach().reshape(-1))
-        flat = torch.cat([v.to("cpu", torch.float64) for v in vals])
-        return (self.train_inputs[0].device, settings.contraction.value(), tuple(flat.tolist()))
+            tensors.append(self.covar_module.outputscale)
+        ident = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        return (self.train_inputs[0].device, settings.contraction.value(), ident)
 
     def _base_kernel(self) -> Kernel:
         k = self.covar_module.base_kernel if isinstance(self.covar_module, ScaleKernel) else self.covar_module
