@@ -41,7 +41,7 @@ constexpr int CT_PER_CTA = 8;  // column tiles swept by one CTA in the slice-emi
 // every entry (fixed exponent: 0 < k <= outputscale < 2^e; same digits as slice_rows_kernel in ozaki_imma.cu) and the
 // per-tile partial sums of K * alpha, so neither the fp64 K nor a separate slicing pass touches HBM.
 template <bool SLICES>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U1, int64_t m1,
                  const double* __restrict__ U2, int m2, int d, double* __restrict__ K, int64_t ldk,
                  int8_t* __restrict__ S, int G, int fixed_exp, const double* __restrict__ alpha,
