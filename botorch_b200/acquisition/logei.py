@@ -66,7 +66,7 @@ class LogImprovementMCAcquisitionFunction(SampleReducingMCAcquisitionFunction):
     # ---- fused-route plumbing -------------------------------------------------------------------
     def _fusable(self, X: Tensor) -> bool:
         return (isinstance(self.model, SingleTaskGP) and self._identity_objective and self.posterior_transform is None
-                and self._constraints is None and X.is_cuda and X.dtype == torch.float64
+                and self._constraints is None and X.is_cuda and X.dtype in (torch.float64, torch.float32)
                 and X.shape[-2] <= _lib.MAX_Q and len(self.sample_shape) == 1
                 and (self.sampler is None or isinstance(self.sampler, NormalMCSampler)))
 
@@ -116,9 +116,9 @@ class qLogExpectedImprovement(LogImprovementMCAcquisitionFunction):
             return self._sample_reduction(self._q_reduction(self._non_reduced_forward(X=X)))
         strat = self.model.prediction_strategy()
         batch_shape = X.shape[:-2]
-        Xf = X.reshape(-1, *X.shape[-2:])
+        Xf = X.reshape(-1, *X.shape[-2:]).to(torch.float64)  # float32 callers: computed in fp64, returned in their dtype
         out = _chunked_fused(Xf, strat, None, self._mc_operands(Xf))
-        return out.reshape(batch_shape)
+        return out.reshape(batch_shape).to(X.dtype)
 
 
 class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCholeskyMCSamplerMixin):
@@ -254,7 +254,7 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
             return self._sample_reduction(self._q_reduction(self._non_reduced_forward(X=X)))
         strat = self.model.prediction_strategy()
         batch_shape = X.shape[:-2]
-        Xf = X.reshape(-1, *X.shape[-2:])
+        Xf = X.reshape(-1, *X.shape[-2:]).to(torch.float64)
         try:
             out = _chunked_fused(Xf, strat, self._baseline_operands(), self._mc_operands(Xf))
         except (NanError, NotPSDError):
@@ -266,7 +266,7 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
                 return self._sample_reduction(self._q_reduction(self._non_reduced_forward(X=X)))
             finally:
                 self._cache_root = cache_root
-        return out.reshape(batch_shape)
+        return out.reshape(batch_shape).to(X.dtype)
 
 
 def _chunked_fused(Xf: Tensor, strat, base, mc, max_rows: int = 1 << 17) -> Tensor:

@@ -127,3 +127,34 @@ def test_error_conventions():
     out = acqf(torch.rand(3, 2, 4, device=DEV, dtype=torch.float64))
     assert out.shape == (3,)
     assert acqf.sampler is not None and acqf.sampler.sample_shape == torch.Size([512])  # lazy default sampler
+
+
+def test_float32_callers_take_the_fused_route_in_fp64():
+    """fp32 optional mode: float32 models / inputs are computed in fp64 on the fused route and
+    returned in the caller's dtype; against the fp64 evaluation of the same (float32-rounded) data the difference is
+    float32 rounding of the output only (tolerance 1e-4 relative, as the north star states for fp32)."""
+    import warnings
+
+    from botorch_b200.acquisition import qLogNoisyExpectedImprovement
+    from botorch_b200.acquisition._fused import LaunchStats
+    from botorch_b200.models import RBFKernel, SingleTaskGP
+    from botorch_b200.sampling import SobolQMCNormalSampler
+
+    X, Y, ls, bounds, g = _data(box=(0.0, 1.0), seed=5)
+    X32, Y32 = X.float(), Y.float()
+    vals, grads = {}, {}
+    for dt in (torch.float32, torch.float64):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = SingleTaskGP(X32.to(DEV, dt), Y32.to(DEV, dt), covar_module=RBFKernel(ard_num_dims=4, lengthscale=ls)).to(DEV)
+        acqf = qLogNoisyExpectedImprovement(model, X_baseline=X32[:8].to(DEV, dt), prune_baseline=False,
+                                            sampler=SobolQMCNormalSampler(torch.Size([64]), seed=1))
+        Xq = torch.rand(6, 2, 4, generator=torch.Generator().manual_seed(1)).to(DEV, dt).requires_grad_(True)
+        before = LaunchStats.launches
+        v = acqf(Xq)
+        (gr,) = torch.autograd.grad(v.sum(), Xq)
+        assert LaunchStats.launches > before  # the fused kernels ran (not the generic torch-op route)
+        assert v.dtype == dt and gr.dtype == dt
+        vals[dt], grads[dt] = v.detach().double().cpu(), gr.double().cpu()
+    assert float(((vals[torch.float32] - vals[torch.float64]).abs() / vals[torch.float64].abs()).max()) < 1e-4
+    assert float((grads[torch.float32] - grads[torch.float64]).abs().max() / grads[torch.float64].abs().max()) < 1e-4
