@@ -6,6 +6,7 @@ from __future__ import annotations
 import warnings
 
 import torch
+import torch.distributed as dist
 from torch import Tensor
 from torch.quasirandom import SobolEngine
 
@@ -103,6 +104,10 @@ def gen_batch_initial_conditions(acq_function, bounds: Tensor, q: int, num_resta
                     acq_vals = torch.cat([acq_function(x_.to(device=device)).cpu() for x_ in X_rnd.split(limit, dim=0)])
             batch_initial_conditions, _ = init_func(X=X_rnd, acq_vals=acq_vals, n=num_restarts, **init_kwargs)
             batch_initial_conditions = batch_initial_conditions.to(device=device)
+            if shard_across_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # the Boltzmann draw of `initialize_q_batch` consumes each process's own global RNG: every rank adopts
+                # rank 0's selection so that the restarts the ranks split are slices of ONE list
+                dist.broadcast(batch_initial_conditions, src=0)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
                 return batch_initial_conditions
             if factor < max_factor:
