@@ -76,3 +76,50 @@ def test_qlognei_optimize_runs_in_bounds():
     assert cand.shape == (3, 20) and (cand >= 0).all() and (cand <= 1).all() and torch.isfinite(val)
     cs, vs = optimize_acqf(acqf, data.bounds.to(dev), q=2, num_restarts=3, raw_samples=32, options=opts, sequential=True)
     assert cs.shape == (2, 20) and vs.shape == (2,) and (cs >= 0).all() and (cs <= 1).all()
+
+
+def test_bo_loop_with_model_rebuilds_and_hyperparameter_updates():
+    """A short closed loop (the way the path is used): build a model from the data, optimise qLogNEI (default baseline
+    pruning, int8 and FP64 contraction alternating), evaluate Hartmann-6, append, repeat.  Guards the cache invalidation
+    of the device prediction strategy: new data and in-place hyper-parameter changes must both be picked up."""
+    from botorch_b200 import settings
+    from botorch_b200.acquisition import qLogNoisyExpectedImprovement
+    from botorch_b200.models import SingleTaskGP
+    from botorch_b200.optim import optimize_acqf
+    from botorch_b200.test_functions import Hartmann
+
+    dev = torch.device("cuda:0")
+    f = Hartmann(dim=6, negate=True)
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(24, 6, generator=g, dtype=torch.float64)
+    Y = f(X).unsqueeze(-1)
+    bounds = torch.stack([torch.zeros(6), torch.ones(6)]).to(dev, torch.float64)
+    best0 = float(Y.max())
+    try:
+        for it in range(3):
+            settings.contraction.set("int8" if it % 2 else "dmma")
+            model = SingleTaskGP(X.to(dev), Y.to(dev))
+            model.likelihood.noise = 1e-3
+            acqf = qLogNoisyExpectedImprovement(model, X_baseline=X.to(dev))
+            torch.manual_seed(it)
+            cand, val = optimize_acqf(acqf, bounds, q=2, num_restarts=6, raw_samples=128, options={"maxiter": 30, "seed": it})
+            assert cand.shape == (2, 6) and (cand >= 0).all() and (cand <= 1).all() and torch.isfinite(val)
+            # the optimiser's value is reproduced by a fresh evaluation of its candidate
+            assert torch.allclose(acqf(cand.unsqueeze(0)).squeeze(0), val, rtol=1e-9, atol=0)
+            X = torch.cat([X, cand.cpu()])
+            Y = torch.cat([Y, f(cand.cpu()).unsqueeze(-1)])
+        assert float(Y.max()) >= best0
+        # in-place hyper-parameter change on a live model: the cached strategy must be rebuilt
+        model = SingleTaskGP(X.to(dev), Y.to(dev))
+        m1 = model.posterior(X[:4].to(dev)).mean.clone()
+        s1 = model.prediction_strategy()
+        assert model.prediction_strategy() is s1  # unchanged state: cached
+        model.covar_module.lengthscale = model.covar_module.lengthscale * 0.5
+        assert model.prediction_strategy() is not s1
+        assert not torch.allclose(model.posterior(X[:4].to(dev)).mean, m1)
+        model.likelihood.noise = 0.05
+        v_hi = model.posterior(X[:4].to(dev)).variance
+        model.likelihood.noise = 1e-4
+        assert (model.posterior(X[:4].to(dev)).variance < v_hi).all()
+    finally:
+        settings.contraction.set("dmma")
