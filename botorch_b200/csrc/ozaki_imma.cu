@@ -328,6 +328,204 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ---- CTA-pair variant (cta_group::2) --------------------------------------------------------------------------------
+// Two CTAs of a cluster (one TPC) work on a 256-row x BN tile: each loads its own 128 rows of the A slices but only HALF of
+// every B slice tile (BN/2 rows), and the leader's `tcgen05.mma.cta_group::2` (M = 256) reads both halves, so the operand
+// bytes an SM has to ingest per output drop from G(128 + BN) to G(128 + BN/2).  The N halves of the two CTAs interleave
+// inside one instruction, so slices cannot be stacked into wide UMMAs here: one M=256 x N=BN instruction per slice pair.
+// Barrier plumbing as in CUTLASS's 2-SM pipelines: both producers signal the LEADER's full barrier (armed by the leader
+// with the bytes of both CTAs), the leader's commits are multicast to both CTAs' empty / accumulator barriers, and both
+// CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+__device__ __forceinline__ uint32_t oz_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void oz_tma_3d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(oz_smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void oz_umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void oz_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(oz_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int OZ_BK, int OZ_BN>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_imma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh, int tri_mode,
+                   int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
+                   const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc, int group_m) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_BH_TILE = (OZ_BN / 2) * OZ_BK;
+  const int stage_bytes = G * (OZ_A_TILE + OZ_BH_TILE);
+  __shared__ __align__(8) uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double s_col[OZ_MAX_BN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
+  const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
+  const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
+  const uint32_t crank = oz_cluster_rank();        // 0 = leader (issues the MMAs), 1 = peer
+  const int64_t cluster_id = blockIdx.x / 2;
+  const int64_t num_clusters = gridDim.x / 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, 8);   // four epilogue warps in each CTA of the pair (only the leader's copy is used)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (both CTAs) =================
+      int64_t it = 0;
+      OzTile tl;
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, 2, 1>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters) {
+        const int row0 = (int)((tl.mt * 2 + crank) * OZ_BM);
+        const int colh0 = tl.nt * OZ_BN + (int)crank * (OZ_BN / 2);
+        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
+          const int s = (int)(it % stages);
+          if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
+          if (crank == 0) oz_mbar_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
+          const uint32_t lbar = oz_mapa(oz_smem_u32(&full_bar[s]), 0);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          for (int p = 0; p < G; p++) oz_tma_3d_2sm(st + p * OZ_A_TILE, &mapA, lbar, kb * OZ_BK, row0, p);
+          for (int q = 0; q < G; q++) oz_tma_3d_2sm(st + G * OZ_A_TILE + q * OZ_BH_TILE, &mapBh, lbar, kb * OZ_BK, colh0, q);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ================= MMA issuer (leader CTA only) =================
+      // D = S32, A = B = signed int8, both K-major, M = 256 over the CTA pair, N = BN
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int64_t it = 0, tile_i = 0;
+      OzTile tl;
+      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, 2, 1>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
+        if (tile_i > 0) {
+          oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
+          const int s = (int)(it % stages);
+          oz_mbar_wait(&full_bar[s], (uint32_t)((it / stages) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint8_t* st = smem + (size_t)s * stage_bytes;
+          const bool first = (kb == tl.kb0);
+#pragma unroll
+          for (int k = 0; k < OZ_BK / 32; k++) {
+            for (int p = 0; p < G; p++) {
+              const uint64_t ad = oz_desc<OZ_BK>(st + p * OZ_A_TILE) + 2 * k;
+              for (int q = 0; q + p < G; q++) {
+                const uint64_t bd = oz_desc<OZ_BK>(st + G * OZ_A_TILE + q * OZ_BH_TILE) + 2 * k;
+                oz_umma2(tmem_base + (uint32_t)((p + q) * OZ_BN), ad, bd, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
+              }
+            }
+          }
+          oz_commit2_mc(&empty_bar[s], (uint16_t)3);
+        }
+        oz_commit2_mc(&acc_full, (uint16_t)3);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5, both CTAs: each drains its own 128 TMEM lanes) =================
+    const int lg = warp & 3;
+    const int r_in_tile = lg * 32 + lane;
+    const int etid = tid - 64;
+    const uint32_t leader_acc_empty = oz_mapa(oz_smem_u32(&acc_empty), 0);
+    int64_t tile_i = 0;
+    OzTile tl;
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, 2, 1>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
+      const int64_t row = (tl.mt * 2 + crank) * OZ_BM + r_in_tile;
+      const int col0 = tl.nt * OZ_BN;
+      for (int c = etid; c < OZ_BN; c += 128) s_col[c] = (col0 + c < N) ? col_scale[col0 + c] : 0.0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool have_acc = tl.kb1 > tl.kb0;
+      if (have_acc) {
+        oz_mbar_wait(&acc_full, (uint32_t)(tile_i & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const bool row_ok = row < M;
+      const double rs = row_ok ? row_scale[row] : 0.0;
+      double* dst = C + (row_ok ? row : 0) * ldc + col0;
+      const bool vec_ok = (ldc & 1) == 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        double acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = 0.0;
+        if (have_acc) {
+          uint32_t v[OZ_MAXG][16];
+#pragma unroll
+          for (int g = 0; g < OZ_MAXG; g++) {
+            if (g < G) {
+              const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN + c0);
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                           : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]), "=r"(v[g][6]),
+                             "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]), "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]),
+                             "=r"(v[g][13]), "=r"(v[g][14]), "=r"(v[g][15])
+                           : "r"(taddr));
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          double w = 1.0 / 4294967296.0;
+#pragma unroll
+          for (int g0 = 0; g0 < OZ_MAXG; g0 += 3) {
+            if (g0 < G) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                const long long s0 = (long long)(int32_t)v[g0][j];
+                const long long s1 = (g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1][j] : 0ll;
+                const long long s2 = (g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2][j] : 0ll;
+                const long long tt = s0 * 65536ll + s1 * 256ll + s2;
+                const double dd = __longlong_as_double(0x4338000000000000ll + tt) - 6755399441055744.0;
+                acc[j] = fma(w, dd, acc[j]);
+              }
+              w *= (1.0 / 16777216.0);
+            }
+          }
+        }
+        if (row_ok && col0 + c0 < N) {
+          if (col0 + c0 + 16 <= N && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2)
+              __stcs(reinterpret_cast<double2*>(dst + c0 + j),
+                     make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]));
+          } else {
+            for (int j = 0; j < 16; j++) if (col0 + c0 + j < N) dst[c0 + j] = acc[j] * rs * s_col[c0 + j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive_remote(leader_acc_empty);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ---- slicing ------------------------------------------------------------------------------------------------------
 // X[rows x K] (fp64, pitch ldx) -> G int8 slices [G][rows][Kp] (Kp = slice pitch >= K, zero padded) and the row scale
 // 2^(e+2) with |x| < 2^e.  fixed_exp != INT_MIN: use that exponent for every row (K(X, X_train) <= outputscale).
@@ -454,6 +652,46 @@ static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri
   return 0;
 }
 
+template <int BN>
+static int oz_launch2_t(const CUtensorMap& mapA, const CUtensorMap& mapBh, int tri_mode, int64_t M, int N, int K, int G,
+                        int stages, size_t smem, size_t smem_budget, const double* row_scale, const double* col_scale, double* C,
+                        int64_t ldc, cudaStream_t st) {
+  auto kern = ozaki_imma2_kernel<64, BN>;
+  static int max_clusters = -1;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cfg.gridDim = dim3(sms / 2 * 2);
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return e != cudaSuccess ? (int)e : MCACQ_ELIMIT; }
+    max_clusters = n;
+  }
+  const int group_m = (getenv("MCACQ_OZ_GROUP") != nullptr) ? atoi(getenv("MCACQ_OZ_GROUP")) : OZ_GROUP_M;
+  const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
+  const int64_t n_tiles = (N + BN - 1) / BN;
+  const int64_t ctiles = ((m_tiles + 1) / 2) * n_tiles;
+  const int nclusters = (int)(ctiles < max_clusters ? ctiles : max_clusters);
+  cfg.gridDim = dim3(nclusters * 2);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapBh, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc, group_m);
+  count_launch();
+  if (e != cudaSuccess) return (int)e;
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
 static int oz_launch(int bk, int bn, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M,
                      int N, int K, int G, int stages, size_t smem, size_t smem_budget, const double* row_scale,
                      const double* col_scale, double* C, int64_t ldc, cudaStream_t st) {
@@ -508,6 +746,24 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   if (stages > OZ_MAX_STAGES) stages = OZ_MAX_STAGES;
   if (stages < 1) return MCACQ_ELIMIT;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const int cta2 = (getenv("MCACQ_OZ_CTA2") != nullptr) ? atoi(getenv("MCACQ_OZ_CTA2")) : 0;
+  if (cta2 && (bn == 64 || bn == 80 || bn == 96 || bn == 128)) {
+    // CTA-pair variant: 64-byte k-blocks, half B tiles per CTA
+    const size_t sb = (size_t)G * (OZ_BM + bn / 2) * 64;
+    int st2 = (int)(smem_budget / sb);
+    if (st2 > OZ_MAX_STAGES) st2 = OZ_MAX_STAGES;
+    if (st2 < 1) return MCACQ_ELIMIT;
+    CUtensorMap mA, mBh;
+    int rc2;
+    if ((rc2 = oz_make_map(&mA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, 64))) return rc2;
+    if ((rc2 = oz_make_map(&mBh, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(bn / 2), 64))) return rc2;
+    const size_t sm2 = (size_t)st2 * sb + 1024;
+    cudaStream_t s2 = (cudaStream_t)stream;
+    if (bn == 64) return oz_launch2_t<64>(mA, mBh, tri_mode, M, N, K, G, st2, sm2, smem_budget, row_scale, col_scale, C, ldc, s2);
+    if (bn == 80) return oz_launch2_t<80>(mA, mBh, tri_mode, M, N, K, G, st2, sm2, smem_budget, row_scale, col_scale, C, ldc, s2);
+    if (bn == 96) return oz_launch2_t<96>(mA, mBh, tri_mode, M, N, K, G, st2, sm2, smem_budget, row_scale, col_scale, C, ldc, s2);
+    return oz_launch2_t<128>(mA, mBh, tri_mode, M, N, K, G, st2, sm2, smem_budget, row_scale, col_scale, C, ldc, s2);
+  }
   CUtensorMap mapA, mapB;
   int rc;
   if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk))) return rc;
