@@ -363,6 +363,24 @@ def main():
 
             ms = time_launch(fn, 2 * args.steps)
             ach = alg_flops / (ms * 1e-3) * 1e-12
+            # what the vendor library reaches for int8 x int8 -> int32 on this part (cuBLASLt via torch._int_mm, 8192^3,
+            # best of 5): 2.5-2.9 POP/s measured, i.e. 1.55-1.8x the bf16 rate rather than the nominal 2x
+            lib_int8 = None
+            try:
+                ai = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=dev)
+                bi = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=dev)
+                best_i = 1e9
+                for _ in range(6):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    torch._int_mm(ai, bi)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    best_i = min(best_i, e0.elapsed_time(e1))
+                lib_int8 = 2.0 * 8192**3 / (best_i * 1e-3) * 1e-12
+                del ai, bi
+            except Exception:  # noqa: BLE001 -- informational only
+                lib_int8 = None
             # roofline of THIS algorithm on the INT8 tensor pipe: every fp64 multiply-add costs G(G+1)/2 int8 multiply-adds;
             # dense int8 peak of the part = 2 x the measured dense bf16 peak
             peak_equiv = 2.0 * bf16_peak / pairs
@@ -370,6 +388,8 @@ def main():
                     "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.59e9 * (M / 65536.0),
                     "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
                     "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
+                    "library_int8_gemm_tops_measured": lib_int8,
+                    "frac_of_library_int8_gemm": (ach * pairs / lib_int8) if lib_int8 else None,
                     "fp64_dgemm_peak_measured": fp64_peak_tf,
                     "traffic_source": "ncu --set full dram__bytes_read+write of the forward launch at M=65536 (6.47 + 2.12 GB, "
                                       "profiles/r01_ncu_full_int8_mode.md; algorithmic: 1.7 GB slices + 2.15 GB output), scaled to this M"}
