@@ -180,9 +180,13 @@ __device__ __forceinline__ void lse_merge(double& m, double& s, double m2, doubl
 __device__ __forceinline__ int coef_pitch(int q) { return (q + 1) & ~1; }
 
 // Forward -------------------------------------------------------------------------------------------
-template <int QMAX, int NS>
-__global__ void __launch_bounds__(SR_THREADS)
+// W > 1 ("wide", for the few q-batches of an optimiser round): W x 128 threads evaluate the per-sample utilities, park them
+// in shared memory, and the first 128 threads then fold them in exactly the order of the W = 1 kernel -- results are
+// bit-identical for every W, only the latency per q-batch changes.
+template <int QMAX, int NS, int W>
+__global__ void __launch_bounds__(SR_THREADS * W)
 sample_reduce_fwd_kernel(SRParams p) {
+  constexpr int NT = SR_THREADS * W, NW = SR_WARPS * W;
   extern __shared__ __align__(16) double sm[];
   const int q = p.q, r = p.r, S = p.S;
   const int QP = coef_pitch(q);
@@ -192,20 +196,21 @@ sample_reduce_fwd_kernel(SRParams p) {
                                                     //  which must not alias T or the jitter retries would re-read garbage)
   double* smean = Tm + q * q;                  // [q]
   double* red = smean + q;                     // [2 * SR_WARPS]
+  double* fmv = red + 2 * SR_WARPS;            // [S] per-sample utilities (W > 1 only)
   __shared__ int s_info;
   __shared__ int s_nonfinite;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t bb = blockIdx.x;
 
-  for (int idx = tid; idx < q * r; idx += SR_THREADS) brow[idx] = p.Sxb[bb * q * r + idx];
-  for (int idx = tid; idx < q; idx += SR_THREADS) smean[idx] = p.mean[bb * q + idx];
-  for (int idx = tid; idx < (r + q) * QP; idx += SR_THREADS) coefT[idx] = 0.0;
+  for (int idx = tid; idx < q * r; idx += NT) brow[idx] = p.Sxb[bb * q * r + idx];
+  for (int idx = tid; idx < q; idx += NT) smean[idx] = p.mean[bb * q + idx];
+  for (int idx = tid; idx < (r + q) * QP; idx += NT) coefT[idx] = 0.0;
   if (tid == 0) { s_info = 0; s_nonfinite = 0; }
   __syncthreads();
 
   // ---- B = Sxb L^{-T}: forward substitution, one warp per row, lanes over the dot product
-  for (int i = warp; i < q; i += SR_WARPS) {
+  for (int i = warp; i < q; i += NW) {
     double* bi = brow + (size_t)i * r;
     for (int j = 0; j < r; j++) {
       const double* Lj = p.L_base + (size_t)j * r;
@@ -218,14 +223,14 @@ sample_reduce_fwd_kernel(SRParams p) {
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+  for (int idx = tid; idx < q * r; idx += NT) {
     const int i = idx / r, j = idx - i * r;
     const double v = brow[idx];
     coefT[j * QP + i] = v;
     p.Bm[bb * q * r + idx] = v;
   }
   // ---- T = Sxx - B B^T (lower triangle)
-  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+  for (int idx = tid; idx < q * q; idx += NT) {
     const int i = idx / q, j = idx - i * q;
     double v = 0.0;
     if (j <= i) {
@@ -284,61 +289,107 @@ sample_reduce_fwd_kernel(SRParams p) {
   const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
   double lm = -CUDART_INF, ls = 0.0;
   bool nonfinite = false;
-  for (int s0 = tid * NS; s0 < S; s0 += SR_THREADS * NS) {
-    double y[NS][QMAX];
+  if (W > 1) {
+    static_assert(W == 1 || NS == 1, "the wide kernel evaluates one sample per thread and pass");
+    for (int s0 = tid; s0 < S; s0 += NT) {
+      double y[QMAX];
 #pragma unroll
-    for (int ns = 0; ns < NS; ns++)
-#pragma unroll
-      for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+      for (int i = 0; i < QMAX; i++) y[i] = 0.0;
 #pragma unroll 4
-    for (int j = 0; j < r + q; j++) {
-      double z[NS];
+      for (int j = 0; j < r + q; j++) {
+        const double z = p.Zt[(size_t)j * S + s0];
+        const double* cj = coefT + j * QP;
 #pragma unroll
-      for (int ns = 0; ns < NS; ns++) z[ns] = (s0 + ns < S) ? p.Zt[(size_t)j * S + s0 + ns] : 0.0;
-      const double* cj = coefT + j * QP;
-#pragma unroll
-      for (int i = 0; i < QMAX; i += 2) {
-        if (i < q) {
-          const double2 c2 = *reinterpret_cast<const double2*>(cj + i);
-#pragma unroll
-          for (int ns = 0; ns < NS; ns++) {
-            y[ns][i] = fma(c2.x, z[ns], y[ns][i]);
-            if (i + 1 < QMAX) y[ns][i + 1] = fma(c2.y, z[ns], y[ns][i + 1]);
+        for (int i = 0; i < QMAX; i += 2) {
+          if (i < q) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cj + i);
+            y[i] = fma(c2.x, z, y[i]);
+            if (i + 1 < QMAX) y[i + 1] = fma(c2.y, z, y[i + 1]);
           }
         }
       }
+      const double bst = p.best[s0];
+      double li[QMAX], wdummy[QMAX];
+#pragma unroll
+      for (int i = 0; i < QMAX; i++) {
+        if (i < q) {
+          const double yi = y[i] + smean[i];
+          if (!isfinite(yi)) nonfinite = true;
+          double dl;
+          li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
+        } else li[i] = -CUDART_INF;
+      }
+      fmv[s0] = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
     }
-#pragma unroll
-    for (int ns = 0; ns < NS; ns++) {
-      if (s0 + ns < S) {
-        const double bst = p.best[s0 + ns];
-        double li[QMAX], wdummy[QMAX];
-#pragma unroll
-        for (int i = 0; i < QMAX; i++) {
-          if (i < q) {
-            const double yi = y[ns][i] + smean[i];
-            if (!isfinite(yi)) nonfinite = true;
-            double dl;
-            li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
-          } else li[i] = -CUDART_INF;
-        }
-        const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
-        if (p.fat >= 2) ls += fm;  // plain mean over the samples
+    if (nonfinite) s_nonfinite = 1;
+    __syncthreads();
+    if (tid < SR_THREADS) {
+      for (int s0 = tid; s0 < S; s0 += SR_THREADS) {   // the W = 1 kernel's per-thread sample order
+        const double fm = fmv[s0];
+        if (p.fat >= 2) ls += fm;
         else if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
         else lse_push(lm, ls, fm);
+      }
+    }
+  } else {
+  for (int s0 = tid * NS; s0 < S; s0 += SR_THREADS * NS) {
+      double y[NS][QMAX];
+#pragma unroll
+      for (int ns = 0; ns < NS; ns++)
+#pragma unroll
+        for (int i = 0; i < QMAX; i++) y[ns][i] = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < r + q; j++) {
+        double z[NS];
+#pragma unroll
+        for (int ns = 0; ns < NS; ns++) z[ns] = (s0 + ns < S) ? p.Zt[(size_t)j * S + s0 + ns] : 0.0;
+        const double* cj = coefT + j * QP;
+#pragma unroll
+        for (int i = 0; i < QMAX; i += 2) {
+          if (i < q) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cj + i);
+#pragma unroll
+            for (int ns = 0; ns < NS; ns++) {
+              y[ns][i] = fma(c2.x, z[ns], y[ns][i]);
+              if (i + 1 < QMAX) y[ns][i + 1] = fma(c2.y, z[ns], y[ns][i + 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int ns = 0; ns < NS; ns++) {
+        if (s0 + ns < S) {
+          const double bst = p.best[s0 + ns];
+          double li[QMAX], wdummy[QMAX];
+#pragma unroll
+          for (int i = 0; i < QMAX; i++) {
+            if (i < q) {
+              const double yi = y[ns][i] + smean[i];
+              if (!isfinite(yi)) nonfinite = true;
+              double dl;
+              li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
+            } else li[i] = -CUDART_INF;
+          }
+          const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
+          if (p.fat >= 2) ls += fm;  // plain mean over the samples
+          else if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
+          else lse_push(lm, ls, fm);
+        }
       }
     }
   }
   if (nonfinite) s_nonfinite = 1;
   // ---- CTA logsumexp (modes 0/1) or sum (modes >= 2), fixed combination order
+  if (warp < SR_WARPS) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double m2 = __shfl_xor_sync(0xffffffffu, lm, o);
-    const double s2 = __shfl_xor_sync(0xffffffffu, ls, o);
-    if (p.fat >= 2) ls += s2;
-    else lse_merge(lm, ls, m2, s2);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double m2 = __shfl_xor_sync(0xffffffffu, lm, o);
+      const double s2 = __shfl_xor_sync(0xffffffffu, ls, o);
+      if (p.fat >= 2) ls += s2;
+      else lse_merge(lm, ls, m2, s2);
+    }
+    if (lane == 0) { red[2 * warp] = lm; red[2 * warp + 1] = ls; }
   }
-  if (lane == 0) { red[2 * warp] = lm; red[2 * warp + 1] = ls; }
   __syncthreads();
   if (tid == 0) {
     double m = red[0], s = red[1];
@@ -358,9 +409,12 @@ sample_reduce_fwd_kernel(SRParams p) {
 }
 
 // Backward ------------------------------------------------------------------------------------------
-template <int QMAX, int NS>
-__global__ void __launch_bounds__(SR_THREADS)
+// W > 1: the per-sample weights (pass A, the expensive part) are evaluated by W x 128 threads; the contraction with the
+// base samples (pass B) keeps the 4-warp split of the W = 1 kernel, so the results are bit-identical for every W.
+template <int QMAX, int NS, int W>
+__global__ void __launch_bounds__(SR_THREADS * W)
 sample_reduce_bwd_kernel(SRParams p, int chunk) {
+  constexpr int NT = SR_THREADS * W, NW = SR_WARPS * W;
   extern __shared__ __align__(16) double sm[];
   const int q = p.q, r = p.r, S = p.S;
   const int QP = coef_pitch(q);
@@ -375,15 +429,15 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t bb = blockIdx.x;
 
-  for (int idx = tid; idx < (r + q) * QP; idx += SR_THREADS) coefT[idx] = 0.0;
-  for (int idx = tid; idx < q * NC; idx += SR_THREADS) gco[idx] = 0.0;
-  for (int idx = tid; idx < q; idx += SR_THREADS) smean[idx] = p.mean[bb * q + idx];
+  for (int idx = tid; idx < (r + q) * QP; idx += NT) coefT[idx] = 0.0;
+  for (int idx = tid; idx < q * NC; idx += NT) gco[idx] = 0.0;
+  for (int idx = tid; idx < q; idx += NT) smean[idx] = p.mean[bb * q + idx];
   __syncthreads();
-  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+  for (int idx = tid; idx < q * r; idx += NT) {
     const int i = idx / r, j = idx - i * r;
     coefT[j * QP + i] = p.Bm[bb * q * r + idx];
   }
-  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+  for (int idx = tid; idx < q * q; idx += NT) {
     const int i = idx / q, j = idx - i * q;
     coefT[(r + j) * QP + i] = p.Cm[bb * q * q + idx];
   }
@@ -398,7 +452,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   for (int c0 = 0; c0 < S; c0 += chunk) {
     const int cend = (c0 + chunk < S) ? c0 + chunk : S;
     // ---- pass A: per-sample weights gy[s][i]
-    for (int s0 = c0 + tid * NS; s0 < cend; s0 += SR_THREADS * NS) {
+    for (int s0 = c0 + tid * NS; s0 < cend; s0 += NT * NS) {
       double y[NS][QMAX];
 #pragma unroll
       for (int ns = 0; ns < NS; ns++)
@@ -448,7 +502,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
     {
       const int nloc = cend - c0;
       const int npad = (nloc + 3) & ~3;
-      for (int idx = tid; idx < (npad - nloc) * GP; idx += SR_THREADS) gy[(size_t)nloc * GP + idx] = 0.0;
+      for (int idx = tid; idx < (npad - nloc) * GP; idx += NT) gy[(size_t)nloc * GP + idx] = 0.0;
     }
     __syncthreads();
     // ---- pass B (tensor pipe): gco[i][j] += sum_s gy[s][i] * Z[s][j]   (j == r+q: the mean column, Z == 1)
@@ -467,37 +521,39 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
         const int j = nj * 8 + g;
         const double* zr = (j < r + q) ? p.Zt + (size_t)j * S + c0 : nullptr;
         const double bconst = (j == r + q) ? 1.0 : 0.0;
-        double acc[MT][2];
+        if (warp < SR_WARPS) {
+          double acc[MT][2];
 #pragma unroll
-        for (int mi = 0; mi < MT; mi++) { acc[mi][0] = 0.0; acc[mi][1] = 0.0; }
-        // four k-steps per trip with all operand loads issued first (the base samples come straight from L2)
-        for (int kk = k_begin; kk < k_end; kk += 4) {
-          double bv[4], av[4][MT];
+          for (int mi = 0; mi < MT; mi++) { acc[mi][0] = 0.0; acc[mi][1] = 0.0; }
+          // four k-steps per trip with all operand loads issued first (the base samples come straight from L2)
+          for (int kk = k_begin; kk < k_end; kk += 4) {
+            double bv[4], av[4][MT];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int sl = 4 * (kk + u) + t4;
-            const bool live = (kk + u < k_end) && sl < nloc;
-            bv[u] = (zr != nullptr) ? (live ? zr[sl] : 0.0) : ((kk + u < k_end) ? bconst : 0.0);
+            for (int u = 0; u < 4; u++) {
+              const int sl = 4 * (kk + u) + t4;
+              const bool live = (kk + u < k_end) && sl < nloc;
+              bv[u] = (zr != nullptr) ? (live ? zr[sl] : 0.0) : ((kk + u < k_end) ? bconst : 0.0);
 #pragma unroll
-            for (int mi = 0; mi < MT; mi++) {
-              const int i = mi * 8 + g;
-              av[u][mi] = (live && i < q) ? gy[(size_t)sl * GP + i] : 0.0;
+              for (int mi = 0; mi < MT; mi++) {
+                const int i = mi * 8 + g;
+                av[u][mi] = (live && i < q) ? gy[(size_t)sl * GP + i] : 0.0;
+              }
             }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int mi = 0; mi < MT; mi++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[mi][0]), "+d"(acc[mi][1]) : "d"(av[u][mi]), "d"(bv[u]));
           }
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int mi = 0; mi < MT; mi++)
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                           : "+d"(acc[mi][0]), "+d"(acc[mi][1]) : "d"(av[u][mi]), "d"(bv[u]));
-        }
-#pragma unroll
-        for (int mi = 0; mi < MT; mi++) {
-          stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4] = acc[mi][0];
-          stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4 + 1] = acc[mi][1];
+          for (int mi = 0; mi < MT; mi++) {
+            stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4] = acc[mi][0];
+            stage[((warp * QMAX) + mi * 8 + g) * 8 + 2 * t4 + 1] = acc[mi][1];
+          }
         }
         __syncthreads();
-        for (int o = tid; o < QMAX * 8; o += SR_THREADS) {
+        for (int o = tid; o < QMAX * 8; o += NT) {
           const int i = o >> 3, jj = nj * 8 + (o & 7);
           if (i < q && jj < NC) {
             double a = 0.0;
@@ -517,7 +573,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   double* Xm = mats + q * q;
   double* Gm = mats + 2 * q * q;
   double* gT = mats + 3 * q * q;
-  for (int idx = tid; idx < q * q; idx += SR_THREADS) {
+  for (int idx = tid; idx < q * q; idx += NT) {
     const int i = idx / q, j = idx - i * q;
     Lm[idx] = (j <= i) ? coefT[(r + j) * QP + i] : 0.0;
   }
@@ -559,9 +615,9 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   }
   __syncthreads();
   // ---- outputs: gmean, gSxx = gT, gB_tot = gB - 2 gT B
-  for (int idx = tid; idx < q; idx += SR_THREADS) p.gmean[bb * q + idx] = gco[idx * NC + r + q];
-  for (int idx = tid; idx < q * q; idx += SR_THREADS) p.gSxx[bb * q * q + idx] = gT[idx];
-  for (int idx = tid; idx < q * r; idx += SR_THREADS) {
+  for (int idx = tid; idx < q; idx += NT) p.gmean[bb * q + idx] = gco[idx * NC + r + q];
+  for (int idx = tid; idx < q * q; idx += NT) p.gSxx[bb * q * q + idx] = gT[idx];
+  for (int idx = tid; idx < q * r; idx += NT) {
     const int i = idx / r, j = idx - i * r;
     double v = gco[i * NC + j];
     for (int k = 0; k < q; k++) v -= 2.0 * gT[i * q + k] * coefT[j * QP + k];
@@ -569,7 +625,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   }
   __syncthreads();
   // ---- gSxb = gB_tot L_base^{-1}: backward substitution, one warp per row
-  for (int i = warp; i < q; i += SR_WARPS) {
+  for (int i = warp; i < q; i += NW) {
     double* gi = gy + (size_t)i * r;
     for (int j = r - 1; j >= 0; j--) {
       double part = 0.0;
@@ -584,10 +640,17 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
 }
 
 // ---- host launchers --------------------------------------------------------------------------------
-static size_t fwd_smem(int q, int r) {
+static size_t fwd_smem(int q, int r, int S, int wide) {
   int QP = (q + 1) & ~1;
   size_t scratch = (size_t)q * (r > q ? r : q);
-  return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS) * sizeof(double);
+  return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS + (wide ? (size_t)S : 0)) * sizeof(double);
+}
+
+// q-batches below which the wide (4 x 128 threads) variants are used: fewer CTAs than the machine has SM sub-partitions
+constexpr int64_t SR_WIDE_BELOW = 296;
+static bool sr_use_wide(int64_t b) {
+  const char* e = getenv("MCACQ_SR_WIDE");  // test hook: 0 / 1 force the narrow / wide variant (results must not differ)
+  return e != nullptr ? atoi(e) != 0 : b < SR_WIDE_BELOW;
 }
 
 static size_t bwd_smem(int q, int r, int chunk, int qmax) {
@@ -597,19 +660,19 @@ static size_t bwd_smem(int q, int r, int chunk, int qmax) {
           (size_t)SR_WARPS * qmax * 8) * sizeof(double);
 }
 
-template <int QMAX, int NS>
+template <int QMAX, int NS, int W>
 static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
-  size_t smem = fwd_smem(p.q, p.r);
+  size_t smem = fwd_smem(p.q, p.r, p.S, W > 1);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
-  auto kern = sample_reduce_fwd_kernel<QMAX, NS>;
+  auto kern = sample_reduce_fwd_kernel<QMAX, NS, W>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(unsigned)p.b, SR_THREADS, smem, st>>>(p);
+  kern<<<(unsigned)p.b, SR_THREADS * W, smem, st>>>(p);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
-template <int QMAX, int NS>
+template <int QMAX, int NS, int W>
 static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
   int chunk = (36 * 1024) / (8 * (p.q | 1));
@@ -619,9 +682,9 @@ static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   if ((int64_t)chunk * (p.q | 1) < (int64_t)p.q * p.r) chunk = (p.q * p.r + (p.q | 1) - 1) / (p.q | 1);
   size_t smem = bwd_smem(p.q, p.r, chunk, QMAX);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
-  auto kern = sample_reduce_bwd_kernel<QMAX, NS>;
+  auto kern = sample_reduce_bwd_kernel<QMAX, NS, W>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(unsigned)p.b, SR_THREADS, smem, st>>>(p, chunk);
+  kern<<<(unsigned)p.b, SR_THREADS * W, smem, st>>>(p, chunk);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
@@ -632,17 +695,19 @@ int sample_reduce_fwd(const SRParams& p, cudaStream_t st) {
   if (p.b == 0) return 0;
   // one sample per thread and pass: more resident warps beat per-thread ILP here (the transcendental chains do not
   // interleave across samples): 1.55 -> 0.96 ms forward, 2.86 -> 1.83 ms backward per C3 chunk
-  if (p.q <= 8) return launch_sr_fwd<8, 1>(p, st);
-  if (p.q <= 16) return launch_sr_fwd<16, 1>(p, st);
-  return launch_sr_fwd<32, 1>(p, st);
+  const bool wide = sr_use_wide(p.b);
+  if (p.q <= 8) return wide ? launch_sr_fwd<8, 1, 4>(p, st) : launch_sr_fwd<8, 1, 1>(p, st);
+  if (p.q <= 16) return wide ? launch_sr_fwd<16, 1, 4>(p, st) : launch_sr_fwd<16, 1, 1>(p, st);
+  return launch_sr_fwd<32, 1, 1>(p, st);
 }
 
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st) {
   if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
   if (p.b == 0) return 0;
-  if (p.q <= 8) return launch_sr_bwd<8, 1>(p, st);
-  if (p.q <= 16) return launch_sr_bwd<16, 1>(p, st);
-  return launch_sr_bwd<32, 1>(p, st);
+  const bool wide = sr_use_wide(p.b);
+  if (p.q <= 8) return wide ? launch_sr_bwd<8, 1, 4>(p, st) : launch_sr_bwd<8, 1, 1>(p, st);
+  if (p.q <= 16) return launch_sr_bwd<16, 1, 1>(p, st);
+  return launch_sr_bwd<32, 1, 1>(p, st);
 }
 
 }  // namespace mcacq

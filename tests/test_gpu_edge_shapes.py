@@ -173,3 +173,35 @@ def test_chunk_boundary_is_invisible():
     v_o, g_o = value_and_grad(OracleQLogNEI(gp, Xb, 32, 3), Xq[idx].cpu())
     assert float(((v.detach()[idx].cpu() - v_o).abs() / v_o.abs()).max()) < 1e-8
     assert float((gr[idx].cpu() - g_o).abs().max() / g_o.abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("contraction", ["dmma", "int8"])
+def test_wide_and_narrow_sample_reduce_are_bit_identical(contraction, monkeypatch):
+    """Optimiser rounds (b < 296 q-batches) run the sample/reduce kernels with 4 x 128 threads per q-batch, sweeps with
+    128: the per-thread fold order is the same by construction, so values and gradients must agree bit for bit
+    (this is what keeps a t-batch's result independent of how it is chunked or sharded)."""
+    from botorch_b200 import settings
+    from botorch_b200.acquisition import qExpectedImprovement, qLogExpectedImprovement, qLogNoisyExpectedImprovement
+    from botorch_b200.sampling import SobolQMCNormalSampler
+
+    try:
+        model, gp, X, Y, g = _pair(90, 4, "matern52", 3, contraction)
+        Xb = torch.rand(11, 4, generator=g, dtype=torch.float64).to(DEV)
+        mk = lambda S: SobolQMCNormalSampler(torch.Size([S]), seed=2)
+        cases = [(qLogNoisyExpectedImprovement(model, X_baseline=Xb, prune_baseline=False, sampler=mk(1024)), 8),
+                 (qLogExpectedImprovement(model, best_f=float(Y.max()), sampler=mk(200)), 3),
+                 (qLogExpectedImprovement(model, best_f=float(Y.max()), sampler=mk(512), fat=False), 12),
+                 (qExpectedImprovement(model, best_f=float(Y.median()), sampler=mk(300)), 5)]
+        for acqf, q in cases:
+            Xq = torch.rand(9, q, 4, generator=g, dtype=torch.float64).to(DEV)
+            out = {}
+            for wide in ("0", "1"):
+                monkeypatch.setenv("MCACQ_SR_WIDE", wide)
+                Xg = Xq.clone().requires_grad_(True)
+                v = acqf(Xg)
+                (gr,) = torch.autograd.grad(v.sum(), Xg)
+                out[wide] = (v.detach().clone(), gr.clone())
+            assert torch.equal(out["0"][0], out["1"][0]) and torch.equal(out["0"][1], out["1"][1])
+            assert torch.isfinite(out["1"][0]).all()
+    finally:
+        settings.contraction.set("dmma")
