@@ -175,8 +175,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")   # (the banner is printed at every level >= VERSION)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lo, hi = shard_bounds(b_total, rank, world)
     b_local = hi - lo

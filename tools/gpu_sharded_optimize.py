@@ -9,8 +9,8 @@ from botorch_b200.optim import optimize_acqf
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ.pop("NCCL_DEBUG")
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 ok = True
