@@ -131,6 +131,7 @@ class DevicePredictionStrategy:
     # When K is so ill-conditioned that the variance collapses by more than ~5 orders of magnitude everywhere, the digits
     # the fp64 contraction keeps are lost: the probe below detects that and switches the model to 'dmma'.
     INT8_PROBE_TOL = 1e-7
+    INT8_PROBE_GRAD_TOL = 1e-6   # gradient of the probe variances (C1-C3 measure ~1e-8)
 
     def _guard_int8(self, Xt: Tensor) -> None:
         """Probe the int8 contraction against the FP64 one on this model (training points: smallest posterior variances,
@@ -143,21 +144,38 @@ class DevicePredictionStrategy:
         box = lo + (hi - lo) * torch.rand(256, self.d, generator=g, dtype=torch.float64).to(Xt.device)
         probe = torch.cat([Xt[take], box]) * self.x_coef + self.x_offset  # back to the raw input space
         probe = probe.unsqueeze(1)  # P x 1 x d
-        _, v8 = self.posterior_blocks(probe)
+        v8, g8 = self._probe_variance_and_grad(probe)
         self.desc.contraction = 0
-        _, v64 = self.posterior_blocks(probe)
+        v64, g64 = self._probe_variance_and_grad(probe)
         floor = 1e-8 * self.y_std * self.y_std * self.outputscale
         err = float(((v8 - v64).abs() / v64.abs().clamp_min(floor)).max())
-        self.int8_probe_error = err
-        if err <= self.INT8_PROBE_TOL:
+        gerr = float((g8 - g64).abs().max() / g64.abs().max().clamp_min(1e-300))
+        self.int8_probe_error, self.int8_probe_grad_error = err, gerr
+        if err <= self.INT8_PROBE_TOL and gerr <= self.INT8_PROBE_GRAD_TOL:
             self.desc.contraction = 1
             return
-        warnings.warn(f"int8 contraction disabled for this model: posterior variance differs by {err:.1e} (relative) from "
-                      "the FP64 contraction on the probe set (ill-conditioned train covariance); using 'dmma'.",
-                      NumericalWarning, stacklevel=3)
+        warnings.warn(f"int8 contraction disabled for this model: on the probe set the posterior variance differs by {err:.1e} "
+                      f"and its gradient by {gerr:.1e} (relative) from the FP64 contraction (ill-conditioned train "
+                      "covariance); using 'dmma'.", NumericalWarning, stacklevel=3)
         self.contraction = "dmma"
         self.Rt_slices = self.Rt_scale = self.R_slices = self.R_scale = None
         self.desc.Rt_slices = self.desc.Rt_scale = self.desc.R_slices = self.desc.R_scale = None
+
+    def _probe_variance_and_grad(self, probe: Tensor) -> tuple[Tensor, Tensor]:
+        """Posterior variance at P single points and d(sum of variances)/dX through the forward AND backward contraction of
+        the current mode (the backward one uses one slice less, so it is the first to lose digits)."""
+        P = probe.shape[0]
+        L, st = _lib.lib(), _lib.stream_ptr()
+        f64 = dict(device=self.device, dtype=torch.float64)
+        X = probe.contiguous()
+        mean, covar, gX = torch.empty(P, 1, **f64), torch.empty(P, 1, 1, **f64), torch.empty(P, 1, self.d, **f64)
+        ws = self.workspace(P, 1, 0)
+        _lib.check(L.mcacq_posterior(C.byref(self.desc), X.data_ptr(), P, 1, mean.data_ptr(), covar.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), st), "mcacq_posterior (probe)")
+        gm, gc = torch.zeros(P, 1, **f64), torch.ones(P, 1, 1, **f64)
+        _lib.check(L.mcacq_posterior_backward(C.byref(self.desc), X.data_ptr(), P, 1, gm.data_ptr(), gc.data_ptr(),
+                                              gX.data_ptr(), ws.data_ptr(), ws.numel(), st), "mcacq_posterior_backward (probe)")
+        return covar.reshape(-1), gX.reshape(P, self.d)
 
     def _slice_rows(self, Mx: Tensor, G: int = 6) -> tuple[Tensor, Tensor]:
         rows, K = Mx.shape
