@@ -89,3 +89,49 @@ def test_random_configuration_matches_oracle(seed):
         assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max().clamp_min(1e-300)) < gtol, c
     finally:
         settings.contraction.set("dmma")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_posterior_and_batch_shapes(seed):
+    """`model.posterior` on multi-dimensional t-batches, non-contiguous / expanded inputs and 2-D `q x d` inputs: mean and
+    full covariance against the oracle, gradients against the oracle's autograd; acquisition values keep the batch shape."""
+    from botorch_b200.acquisition import qLogExpectedImprovement
+    from botorch_b200.models import MaternKernel, RBFKernel, SingleTaskGP
+    from botorch_b200.sampling import SobolQMCNormalSampler
+    from oracle.acquisition import OracleQLogEI
+    from oracle.gp import OracleGP
+
+    g = torch.Generator().manual_seed(5000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    n, d, q = ri(3, 150), ri(1, 12), ri(1, 9)
+    kernel = "rbf" if seed % 2 else "matern52"
+    X = torch.rand(n, d, generator=g, dtype=torch.float64)
+    Y = torch.cos(3 * X.sum(-1, keepdim=True) / d ** 0.5) + 0.05 * torch.randn(n, 1, generator=g, dtype=torch.float64)
+    ls = (0.2 + 0.2 * torch.rand(d, generator=g, dtype=torch.float64)) * d ** 0.5
+    model = SingleTaskGP(X.to(DEV), Y.to(DEV), covar_module=(RBFKernel if kernel == "rbf" else MaternKernel)(ard_num_dims=d, lengthscale=ls)).to(DEV)
+    model.likelihood.noise = 3e-3
+    gp = OracleGP(X, Y, ls, torch.tensor(3e-3, dtype=torch.float64), kernel=kernel)
+    shape = [(), (ri(1, 4),), (ri(1, 3), ri(1, 3)), (2, 1, ri(1, 3))][seed % 4]
+    Xq = torch.rand(*shape, q, d, generator=g, dtype=torch.float64)
+    if seed % 3 == 0 and len(shape) >= 1:  # non-contiguous view of a larger tensor
+        big = torch.rand(*shape, q, 2 * d, generator=g, dtype=torch.float64)
+        Xq = big[..., ::2]
+    Xo = Xq.clone().requires_grad_(True)
+    m_o, c_o = gp.posterior_mvn(Xo if Xo.dim() > 2 else Xo.unsqueeze(0))
+    w = torch.randn(c_o.shape, generator=g, dtype=torch.float64)
+    (g_o,) = torch.autograd.grad((c_o * w).sum() + m_o.sum(), Xo)
+    Xg = Xq.to(DEV).requires_grad_(True)
+    post = model.posterior(Xg)
+    assert post.mean.shape == (*shape, q, 1)
+    cov = post.distribution.covariance_matrix
+    assert float((post.mean.squeeze(-1).detach().cpu().reshape(m_o.shape) - m_o.detach()).abs().max() / m_o.detach().abs().max()) < 1e-9
+    assert float((cov.detach().cpu().reshape(c_o.shape) - c_o.detach()).abs().max() / c_o.detach().abs().max()) < 1e-9
+    (gr,) = torch.autograd.grad((cov.reshape(c_o.shape) * w.to(DEV)).sum() + post.mean.sum(), Xg)
+    assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max()) < 1e-7
+    acqf = qLogExpectedImprovement(model, best_f=float(Y.max()) - 0.1, sampler=SobolQMCNormalSampler(torch.Size([32]), seed=seed))
+    with torch.no_grad():
+        v = acqf(Xq.to(DEV))
+    # (a python-float best_f becomes a float32 buffer in the reference, `torch.as_tensor(best_f)`: same on both sides)
+    v_o = OracleQLogEI(gp, float(Y.max()) - 0.1, 32, seed)(Xq.reshape(-1, q, d)).detach()
+    assert v.shape == (torch.Size(shape) if shape else torch.Size([1]))  # a 2-D `q x d` input is a t-batch of one
+    assert float(((v.cpu().reshape(-1) - v_o).abs() / v_o.abs().clamp_min(1e-12)).max()) < 1e-8
