@@ -135,3 +135,60 @@ def test_random_posterior_and_batch_shapes(seed):
     v_o = OracleQLogEI(gp, float(Y.max()) - 0.1, 32, seed)(Xq.reshape(-1, q, d)).detach()
     assert v.shape == (torch.Size(shape) if shape else torch.Size([1]))  # a 2-D `q x d` input is a t-batch of one
     assert float(((v.cpu().reshape(-1) - v_o).abs() / v_o.abs().clamp_min(1e-12)).max()) < 1e-8
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_utility_modes_and_pending_points(seed):
+    """qEI / qSimpleRegret / qPI / qNEI (utility modes 2-4 of the fused kernels) on random shapes, with pending points
+    appended along q, against the oracle; values relative to the largest value, gradients to the largest gradient."""
+    from botorch_b200.acquisition import (qExpectedImprovement, qNoisyExpectedImprovement, qProbabilityOfImprovement,
+                                          qSimpleRegret)
+    from botorch_b200.models import MaternKernel, RBFKernel, SingleTaskGP
+    from botorch_b200.sampling import SobolQMCNormalSampler
+    from oracle import acquisition as oa
+    from oracle.gp import OracleGP
+
+    g = torch.Generator().manual_seed(9000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    n, d, q, S, b = ri(5, 120), ri(1, 10), ri(1, 7), ri(8, 200), ri(1, 12)
+    kernel = "rbf" if seed % 2 else "matern52"
+    X = torch.rand(n, d, generator=g, dtype=torch.float64)
+    Y = torch.sin(3 * X.sum(-1, keepdim=True) / d ** 0.5) + 0.1 * torch.randn(n, 1, generator=g, dtype=torch.float64)
+    ls = (0.2 + 0.2 * torch.rand(d, generator=g, dtype=torch.float64)) * d ** 0.5
+    model = SingleTaskGP(X.to(DEV), Y.to(DEV), covar_module=(RBFKernel if kernel == "rbf" else MaternKernel)(ard_num_dims=d, lengthscale=ls)).to(DEV)
+    model.likelihood.noise = 5e-3
+    gp = OracleGP(X, Y, ls, torch.tensor(5e-3, dtype=torch.float64), kernel=kernel)
+    best = Y.median()
+    npend = seed % 3  # 0, 1 or 2 pending points
+    P = torch.rand(npend, d, generator=g, dtype=torch.float64) if npend else None
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    Xfull = Xq if P is None else torch.cat([Xq, P.expand(b, npend, d)], dim=-2)
+    mk = lambda: SobolQMCNormalSampler(torch.Size([S]), seed=seed)
+    ei = oa.OracleQLogEI(gp, best, S, seed)
+    kind = seed % 4
+    if kind == 0:
+        acqf, ofn = qExpectedImprovement(model, best_f=best.to(DEV), sampler=mk()), lambda x: oa.oracle_qei(ei, x)
+    elif kind == 1:
+        acqf, ofn = qSimpleRegret(model, sampler=mk()), lambda x: oa.oracle_qsr(ei, x)
+    elif kind == 2:
+        acqf, ofn = (qProbabilityOfImprovement(model, best_f=best.to(DEV), sampler=mk(), tau=5e-2),
+                     lambda x: oa.oracle_qpi(ei, x, tau=5e-2))
+    else:
+        Xb = torch.rand(ri(1, 12), d, generator=g, dtype=torch.float64)
+        nei = oa.OracleQLogNEI(gp, Xb, S, seed)
+        acqf, ofn = (qNoisyExpectedImprovement(model, X_baseline=Xb.to(DEV), prune_baseline=False, sampler=mk()),
+                     lambda x: oa.oracle_qnei(nei, x))
+    if P is not None:
+        acqf.set_X_pending(P.to(DEV))
+    Xo = Xq.clone().requires_grad_(True)
+    v_o = ofn(Xo if P is None else torch.cat([Xo, P.expand(b, npend, d)], dim=-2))
+    g_o = torch.autograd.grad(v_o.sum(), Xo)[0] if v_o.requires_grad and float(v_o.abs().sum()) > 0 else torch.zeros_like(Xq)
+    Xg = Xq.to(DEV).requires_grad_(True)
+    v = acqf(Xg)
+    gr = torch.autograd.grad(v.sum(), Xg)[0]
+    vs = float(v_o.detach().abs().max().clamp_min(1e-12))
+    assert float((v.detach().cpu() - v_o.detach()).abs().max()) / vs < 1e-8
+    gs = float(g_o.abs().max())
+    if gs > 0:
+        assert float((gr.cpu() - g_o).abs().max()) / gs < 1e-6
+    assert Xfull.shape[-2] == q + npend
