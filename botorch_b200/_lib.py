@@ -125,6 +125,10 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
         raise McacqError(f"{name} must be float64 (got {t.dtype}).")
     if not t.is_contiguous():
         raise McacqError(f"{name} must be contiguous.")
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        # the kernels are launched on the CURRENT device's stream (one process per GPU: torch.cuda.set_device(LOCAL_RANK))
+        raise McacqError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "call torch.cuda.set_device(...) or wrap the call in `with torch.cuda.device(...)`.")
 
 
 def ptr(t: torch.Tensor | None) -> int | None:
