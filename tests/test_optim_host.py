@@ -132,3 +132,59 @@ def test_optimize_acqf_joint_and_sequential():
     assert allc.shape == (3, 2, 2) and allv.shape == (3,)
     cs, vs = optimize_acqf(acqf, bounds, q=2, num_restarts=3, raw_samples=32, options={"seed": 0}, sequential=True)
     assert cs.shape == (2, 2) and vs.shape == (2,) and acqf.X_pending is None
+
+
+@pytest.mark.parametrize("driver", ["direct", "threads"])
+def test_batched_lbfgsb_drivers_agree_with_scipy_on_bound_types(driver, monkeypatch):
+    """Unbounded, one-sided, per-problem (N x D x 2) bounds, an iteration cap and a halting callback: both drivers must
+    reproduce scipy.optimize.minimize(method='L-BFGS-B') per problem (bit-identical x, f, nit, nfev)."""
+    from botorch_b200.optim import batched_lbfgs_b as B
+
+    rng = np.random.default_rng(3)
+    N, D = 5, 4
+    c = rng.normal(size=(N, D))
+
+    def func(X, batch_indices):
+        idx = np.array(batch_indices)
+        d = X - c[idx]
+        return (d**4).sum(-1) + 0.5 * (d**2).sum(-1) + np.sin(X).sum(-1), 4 * d**3 + d + np.cos(X)
+
+    def run(**kw):
+        if driver == "threads":
+            return B._run_threads(func, kw["x0"], kw.get("bounds"), kw.get("maxiter", 15000), 10, 2.2204460492503131e-09, 1e-5,
+                                  20, 15000, kw.get("callback"), True)
+        drv = B._direct_driver()
+        assert drv is not None
+        return B._run_direct(drv[0], drv[1], func, kw["x0"], kw.get("bounds"), kw.get("maxiter", 15000), 10,
+                             2.2204460492503131e-09, 1e-5, 20, 15000, kw.get("callback"), True)
+
+    x0 = rng.normal(size=(N, D))
+    per_problem = np.stack([np.stack([c[i] - 0.3 - 0.1 * i, c[i] + 0.2 + 0.05 * i], axis=-1) for i in range(N)])
+    cases = {"unbounded": None, "one_sided": [(None, 0.4), (-0.2, None), (None, None), (-1.0, 1.0)], "per_problem": per_problem}
+    for name, bnds in cases.items():
+        xs, fs, res = run(x0=x0, bounds=bnds, maxiter=60)
+        for i in range(N):
+            bi = None if bnds is None else (bnds[i] if name == "per_problem" else bnds)
+            if isinstance(bi, np.ndarray):
+                bi = [tuple(r) for r in bi]
+            ref = minimize(lambda x, i=i: tuple(v[0] for v in func(x[None], [i])), x0[i], jac=True, method="L-BFGS-B",
+                           bounds=bi, options={"maxiter": 60})
+            assert np.array_equal(ref.x, xs[i]) and ref.fun == fs[i], (name, i)
+            assert ref.nit == res[i].nit and ref.nfev == res[i].nfev and ref.status == res[i].status, (name, i)
+    # iteration cap: status 1 like scipy
+    xs, fs, res = run(x0=x0, bounds=None, maxiter=2)
+    assert all(r.nit == 2 and r.status == 1 and not r.success for r in res)
+    # a callback that halts after the third iterate of every problem
+    seen = []
+
+    def cb(xk):
+        seen.append(xk.copy())
+        if len(seen) % 3 == 0 and driver == "direct":
+            raise StopIteration
+
+    if driver == "direct":
+        xs, fs, res = run(x0=x0[:1], bounds=None, callback=cb)
+        assert res[0].nit == 3 and not res[0].success
+    # infeasible bounds are rejected up front
+    with pytest.raises(ValueError):
+        run(x0=x0, bounds=[(1.0, 0.0)] * D)
