@@ -132,7 +132,10 @@ class SingleTaskGP(Model):
         tensors = [base.lengthscale, self.likelihood.noise, self.mean_module.constant, self.train_inputs[0], self.train_targets]
         if isinstance(self.covar_module, ScaleKernel):
             tensors.append(self.covar_module.outputscale)
-        ident = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        ident = tuple((id(t), t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        # the tensors are kept alive next to the cached strategy (`_strategy_tensors`), so neither their Python identity nor
+        # their storage address can be recycled by a replacement tensor while the key is in use
+        self._key_tensors = tensors
         return (self.train_inputs[0].device, settings.contraction.value(), ident)
 
     def _base_kernel(self) -> Kernel:
@@ -169,6 +172,7 @@ class SingleTaskGP(Model):
             mean_const=float(self.mean_module.constant.detach()), x_offset=offset, x_coef=coef, y_mean=y_mean, y_std=y_std,
             contraction=settings.contraction.value())
         self._strategy_key = key
+        self._strategy_tensors = self._key_tensors
         return self._strategy
 
     def _apply(self, fn, recurse=True):

@@ -123,3 +123,24 @@ def test_bo_loop_with_model_rebuilds_and_hyperparameter_updates():
         assert (model.posterior(X[:4].to(dev)).variance < v_hi).all()
     finally:
         settings.contraction.set("dmma")
+
+
+def test_strategy_cache_sees_replaced_parameter_tensors():
+    """Replacing a hyper-parameter TENSOR (not an in-place update) must invalidate the cached device strategy even if the
+    allocator hands the new tensor the old one's address."""
+    from botorch_b200.models import RBFKernel, SingleTaskGP
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(30, 2, generator=g, dtype=torch.float64).to(dev)
+    Y = torch.sin(4 * X.sum(-1, keepdim=True))
+    model = SingleTaskGP(X, Y, covar_module=RBFKernel(ard_num_dims=2, lengthscale=torch.tensor([0.3, 0.3])))
+    Xq = torch.rand(3, 1, 2, generator=g, dtype=torch.float64).to(dev)
+    seen = []
+    for ls in (0.3, 0.6, 0.3, 0.9):
+        old = model.covar_module.raw_lengthscale
+        model.covar_module.raw_lengthscale = torch.nn.Parameter(torch.full_like(old, ls))
+        del old
+        seen.append(model.posterior(Xq).mean.clone())
+    assert torch.equal(seen[0], seen[2])
+    assert not torch.allclose(seen[0], seen[1]) and not torch.allclose(seen[1], seen[3])
