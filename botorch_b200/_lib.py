@@ -66,7 +66,7 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
+    "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced",
 ]
 
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
     L.mcacq_version.restype = C.c_char_p
     L.mcacq_num_sms.restype = i32
     L.mcacq_last_launch_count.restype = i32
+    L.mcacq_sobol_draw.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     L.mcacq_scale_inputs.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_cov_cross.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp]
     L.mcacq_cov_cross_bwd.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp, vp, vp, i32, vp]

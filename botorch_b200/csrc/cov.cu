@@ -475,3 +475,36 @@ extern "C" int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const doub
                                 /*parts=*/nullptr, st);
 }
 
+
+namespace mcacq {
+__global__ void sobol_draw_kernel(const int64_t* __restrict__ sobolstate, const int64_t* __restrict__ shift, int dim, int64_t n,
+                                  int64_t first_index, double* __restrict__ out) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * dim) return;
+  const int64_t k = idx / dim;
+  const int j = (int)(idx - k * dim);
+  const uint64_t i = (uint64_t)(first_index + k);
+  uint64_t gray = i ^ (i >> 1);
+  int64_t acc = shift[j];
+  const int64_t* row = sobolstate + (int64_t)j * 30;
+  while (gray != 0) {
+    const int b = __ffsll((long long)gray) - 1;
+    if (b < 30) acc ^= row[b];
+    gray &= gray - 1;
+  }
+  out[idx] = (double)acc * 9.31322574615478515625e-10;  // 2^-30, exact
+}
+}  // namespace mcacq
+
+extern "C" int mcacq_sobol_draw(const int64_t* sobolstate, const int64_t* shift, int dim, int64_t n, int64_t first_index,
+                                double* out, void* stream) {
+  using namespace mcacq;
+  if (!sobolstate || !shift || !out || dim <= 0 || n < 0 || first_index < 0) return MCACQ_EINVAL;
+  if (first_index + n > ((int64_t)1 << 30)) return MCACQ_ELIMIT;  // the engine has 30 bits
+  if (n == 0) return 0;
+  const int64_t total = n * dim;
+  sobol_draw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sobolstate, shift, dim, n, first_index, out);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}

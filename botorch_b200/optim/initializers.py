@@ -85,15 +85,20 @@ def gen_batch_initial_conditions(acq_function, bounds: Tensor, q: int, num_resta
         with warnings.catch_warnings(record=True) as ws:
             warnings.simplefilter("always")
             n = raw_samples * factor
+            on_device = False
             if generator is not None:
                 X_rnd = generator(n, q, seed)
             elif effective_dim <= SobolEngine.MAXDIM:
-                X_rnd = draw_sobol_samples(bounds=bounds_cpu, n=n, q=q, seed=seed)
+                # with CUDA bounds the Sobol cloud is generated on the device (bit-identical to the host engine's draw):
+                # no host draw of n*q*d doubles, no H2D copy of them
+                on_device = device.type == "cuda"
+                X_rnd = draw_sobol_samples(bounds=bounds if on_device else bounds_cpu, n=n, q=q, seed=seed)
             else:
                 with manual_seed(seed):
                     X_nlzd = torch.rand(n, q, bounds_cpu.shape[-1], dtype=bounds.dtype)
                 X_rnd = X_nlzd * (bounds_cpu[1] - bounds_cpu[0]) + bounds_cpu[0]
-            X_rnd = X_rnd.cpu()
+            if not on_device:
+                X_rnd = X_rnd.cpu()
             with torch.no_grad():
                 limit = X_rnd.shape[0] if batch_limit is None else batch_limit
                 if shard_across_ranks:
@@ -102,7 +107,14 @@ def gen_batch_initial_conditions(acq_function, bounds: Tensor, q: int, num_resta
                         X_rnd).cpu()
                 else:
                     acq_vals = torch.cat([acq_function(x_.to(device=device)).cpu() for x_ in X_rnd.split(limit, dim=0)])
-            batch_initial_conditions, _ = init_func(X=X_rnd, acq_vals=acq_vals, n=num_restarts, **init_kwargs)
+            if on_device:
+                # the selection (Boltzmann draw from the host RNG, arg-max inclusion) runs on the host exactly as in the
+                # reference, on the values and a row-index proxy; the chosen q-batches are then gathered on the device
+                proxy = torch.arange(X_rnd.shape[0], dtype=torch.float64).view(-1, 1, 1)
+                picked, _ = init_func(X=proxy, acq_vals=acq_vals, n=num_restarts, **init_kwargs)
+                batch_initial_conditions = X_rnd[picked.reshape(-1).long().to(device)]
+            else:
+                batch_initial_conditions, _ = init_func(X=X_rnd, acq_vals=acq_vals, n=num_restarts, **init_kwargs)
             batch_initial_conditions = batch_initial_conditions.to(device=device)
             if shard_across_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 # the Boltzmann draw of `initialize_q_batch` consumes each process's own global RNG: every rank adopts

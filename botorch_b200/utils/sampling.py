@@ -1,8 +1,9 @@
-"""Host-side quasi-random draws with the reference's seed semantics (botorch/utils/sampling.py).
+"""Quasi-random draws with the reference's seed semantics (botorch/utils/sampling.py).
 
-These stay on the host exactly as in the reference (`gen_batch_initial_conditions` keeps `X_rnd` on
-CPU, optim/initializers.py:384): `torch.quasirandom.SobolEngine` is torch's own generator, so a given
-seed yields bit-identical points, which is what makes selected restart indices comparable.
+`torch.quasirandom.SobolEngine` (torch's own generator) does the scrambling, so a given seed yields the reference's
+points bit for bit, which is what makes selected restart indices comparable.  The base samples of the MC samplers are
+drawn on the host once per acquisition function; the `raw_samples x q x d` Sobol cloud of `gen_batch_initial_conditions`
+is generated on the device from the engine's state (`mcacq_sobol_draw`) when the bounds live there.
 """
 from __future__ import annotations
 
@@ -27,12 +28,38 @@ def manual_seed(seed: int | None = None):
             torch.random.set_rng_state(old_state)
 
 
+def _device_sobol(engine: SobolEngine, n: int, device, dtype) -> Tensor:
+    """`engine.draw(n)` of a FRESH engine, generated on `device` by `mcacq_sobol_draw` from the engine's own scrambled
+    direction numbers and shift.  Bit-identical to the host draw: integer XORs scaled by 2^-30; row 0 is the engine's
+    `_first_point`, which torch rounds through its default dtype."""
+    from .. import _lib
+
+    if engine.num_generated != 0:
+        raise ValueError("the device draw reproduces a fresh engine only")
+    out = torch.empty(n, engine.dimension, device=device, dtype=torch.float64)
+    if n == 0:
+        return out.to(dtype)
+    ss = engine.sobolstate.to(device=device, dtype=torch.int64).contiguous()
+    shift = engine.shift.to(device=device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().mcacq_sobol_draw(ss.data_ptr(), shift.data_ptr(), engine.dimension, n, 0, out.data_ptr(),
+                                               _lib.stream_ptr()), "mcacq_sobol_draw")
+    out[0] = engine._first_point.to(dtype).to(device=device, dtype=torch.float64).reshape(-1)
+    return out.to(dtype)
+
+
 def draw_sobol_samples(bounds: Tensor, n: int, q: int, batch_shape=None, seed: int | None = None) -> Tensor:
-    """`n x batch_shape x q x d` scrambled-Sobol points inside `bounds` (reference :74-111)."""
+    """`n x batch_shape x q x d` scrambled-Sobol points inside `bounds` (reference :74-111).  With `bounds` on a CUDA device
+    the points are generated there (same engine, same scrambling, bit-identical values) instead of drawn on the host and
+    copied."""
     batch_shape = torch.Size(batch_shape or ())
     nb = batch_shape.numel()
     d = bounds.shape[-1]
-    raw = SobolEngine(q * d, scramble=True, seed=seed).draw(nb * n, dtype=bounds.dtype)
+    engine = SobolEngine(q * d, scramble=True, seed=seed)
+    if bounds.is_cuda and bounds.dtype in (torch.float64, torch.float32):
+        raw = _device_sobol(engine, nb * n, bounds.device, bounds.dtype)
+    else:
+        raw = engine.draw(nb * n, dtype=bounds.dtype)
     raw = raw.view(*batch_shape, n, q, d).to(device=bounds.device)
     if len(batch_shape) > 0:
         raw = raw.permute(-3, *range(len(batch_shape)), -2, -1)

@@ -191,6 +191,15 @@ int mcacq_log_areas_backward(const void* grad_out, const void* obj_subsets, cons
                              int dtype, double tau_relu, double tau_max, void* grad_obj, void* lcl_workspace,
                              void* stream);
 
+/* Scrambled-Sobol points straight on the device: out[k][j] = (shift[j] XOR_{b in gray(first_index + k)} sobolstate[j][b]) * 2^-30,
+ * gray(i) = i ^ (i >> 1) -- the closed form of the sequence `torch.quasirandom.SobolEngine.draw` produces point by point
+ * (botorch/utils/sampling.py:74-111 `draw_sobol_samples`, called by gen_batch_initial_conditions, optim/initializers.py:425-447).
+ * `sobolstate` [dim][30] and `shift` [dim] are the engine's own scrambled direction numbers and digital shift (int64, device);
+ * integer arithmetic, so the points are bit-identical to the host engine's (its float32-rounded first point is patched by the
+ * caller).  Replaces the host draw + the H2D copy of `raw_samples x q x d` doubles per `optimize_acqf` call.           */
+int mcacq_sobol_draw(const int64_t* sobolstate, const int64_t* shift, int dim, int64_t n, int64_t first_index, double* out,
+                     void* stream);
+
 /* Number of kernels the last forward/backward call on this thread launched (for bench accounting). */
 int mcacq_last_launch_count(void);
 

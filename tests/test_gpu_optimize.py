@@ -144,3 +144,21 @@ def test_strategy_cache_sees_replaced_parameter_tensors():
         seen.append(model.posterior(Xq).mean.clone())
     assert torch.equal(seen[0], seen[2])
     assert not torch.allclose(seen[0], seen[1]) and not torch.allclose(seen[1], seen[3])
+
+
+def test_device_sobol_draw_is_bit_identical_to_the_host_engine():
+    """`mcacq_sobol_draw` (closed-form Gray-code Sobol from the engine's scrambled state) against
+    `torch.quasirandom.SobolEngine.draw`, and `draw_sobol_samples` with CUDA bounds against CPU bounds."""
+    from torch.quasirandom import SobolEngine
+
+    from botorch_b200.utils.sampling import _device_sobol, draw_sobol_samples
+
+    dev = torch.device("cuda:0")
+    for dim, n, seed in [(160, 4097, 0), (7, 513, 5), (24, 1, 1234), (1, 100, 3), (48, 70000, 11)]:
+        ref = SobolEngine(dim, scramble=True, seed=seed).draw(n, dtype=torch.float64)
+        got = _device_sobol(SobolEngine(dim, scramble=True, seed=seed), n, dev, torch.float64)
+        assert torch.equal(ref, got.cpu()), (dim, n, seed)
+    bounds = torch.tensor([[-1.0, 0.0, 2.0], [1.5, 5.0, 2.5]], dtype=torch.float64)
+    a = draw_sobol_samples(bounds=bounds, n=300, q=4, seed=9)
+    b = draw_sobol_samples(bounds=bounds.to(dev), n=300, q=4, seed=9)
+    assert b.is_cuda and torch.equal(a, b.cpu())
