@@ -48,6 +48,23 @@ def _device_sobol(engine: SobolEngine, n: int, device, dtype) -> Tensor:
     return out.to(dtype)
 
 
+_ENGINES: dict[tuple[int, int], SobolEngine] = {}
+
+
+def _fresh_engine(dimension: int, seed: int | None) -> SobolEngine:
+    """A scrambled engine that has not drawn yet.  For an explicit seed the (never advanced) engine is kept: torch spends
+    10-50 ms of host time per construction on the scrambling matrices, and the device draw only reads its state."""
+    if seed is None:
+        return SobolEngine(dimension, scramble=True, seed=None)
+    key = (dimension, int(seed))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        if len(_ENGINES) >= 16:
+            _ENGINES.pop(next(iter(_ENGINES)))
+        eng = _ENGINES[key] = SobolEngine(dimension, scramble=True, seed=seed)
+    return eng
+
+
 def draw_sobol_samples(bounds: Tensor, n: int, q: int, batch_shape=None, seed: int | None = None) -> Tensor:
     """`n x batch_shape x q x d` scrambled-Sobol points inside `bounds` (reference :74-111).  With `bounds` on a CUDA device
     the points are generated there (same engine, same scrambling, bit-identical values) instead of drawn on the host and
@@ -55,11 +72,10 @@ def draw_sobol_samples(bounds: Tensor, n: int, q: int, batch_shape=None, seed: i
     batch_shape = torch.Size(batch_shape or ())
     nb = batch_shape.numel()
     d = bounds.shape[-1]
-    engine = SobolEngine(q * d, scramble=True, seed=seed)
     if bounds.is_cuda and bounds.dtype in (torch.float64, torch.float32):
-        raw = _device_sobol(engine, nb * n, bounds.device, bounds.dtype)
+        raw = _device_sobol(_fresh_engine(q * d, seed), nb * n, bounds.device, bounds.dtype)
     else:
-        raw = engine.draw(nb * n, dtype=bounds.dtype)
+        raw = SobolEngine(q * d, scramble=True, seed=seed).draw(nb * n, dtype=bounds.dtype)
     raw = raw.view(*batch_shape, n, q, d).to(device=bounds.device)
     if len(batch_shape) > 0:
         raw = raw.permute(-3, *range(len(batch_shape)), -2, -1)
