@@ -151,7 +151,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample_b = args.cpu_sample or (128 if spec.n >= 4096 else 512)
+        sample_b = args.cpu_sample or (2048 if spec.n >= 4096 else 8192)   # ~8 s of host work per step on 16 cores
         val, sec, threads, sample = cpu_reference(args, data, spec, args.steps, args.warmup, sample_b)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -400,7 +400,7 @@ def main():
         roofline_alt = roof[other]()
         roofline["step_alg_tflops"] = (2.0 * spec.q * spec.n * spec.n * b_total / world) / (ms_total / args.steps * 1e-3) * 1e-12
         if world == 1:
-            sample_b = args.cpu_sample or (64 if spec.n >= 4096 else 256)
+            sample_b = args.cpu_sample or (2048 if spec.n >= 4096 else 8192)  # ~10 s of host work (bounded sample)
             val, sec, threads, sample = cpu_reference(args, data, spec, 1, 1, sample_b)
             cpu_base = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
