@@ -111,11 +111,15 @@ typedef struct {
 const char* mcacq_version(void);
 int mcacq_num_sms(void);
 
-/* u = ((x - offset) / coef) / lengthscale for `rows` points.                                */
+/* u = ((x - offset) / coef) / lengthscale for `rows` points.  Replaces `Normalize._transform`
+ * (botorch/models/transforms/input.py:541-554, applied by Model.transform_inputs, models/model.py:197-217) and the
+ * `x.div(lengthscale)` of gpytorch's stationary kernels.                                      */
 int mcacq_scale_inputs(const double* X, int64_t rows, int d, const double* x_offset, const double* x_coef,
                        const double* lengthscale, double* U, void* stream);
 
-/* K[i][j] = k(U1[i], U2[j]) for i < m1, j < m2; columns m2..ldk-1 of each row are zero-filled. */
+/* K[i][j] = k(U1[i], U2[j]) for i < m1, j < m2; columns m2..ldk-1 of each row are zero-filled.  Replaces the forward of
+ * gpytorch's RBFKernel / MaternKernel(nu=2.5) / ScaleKernel as configured by botorch/models/utils/gpytorch_modules.py:100-133
+ * and evaluated inside `ExactGP.__call__` (botorch/models/gpytorch.py:585).                      */
 int mcacq_cov_cross(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
                     int d, double* K, int64_t ldk, void* stream);
 
@@ -126,12 +130,16 @@ int mcacq_cov_cross_sliced(int kernel_id, double outputscale, const double* U1, 
                            int d, int64_t ldk, const double* alpha, int G, int fixed_exp, int8_t* slices,
                            double* mean_part, void* stream);
 
-/* dU1[i][:] = sum_j W[i][j] * d k(U1[i], U2[j]) / d U1[i]   (+= if accumulate).             */
+/* dU1[i][:] = sum_j (W[i][j] + row_scale[i] * col_vec[j]) * d k(U1[i], U2[j]) / d U1[i]   (+= if accumulate; row_scale /
+ * col_vec optional).  Replaces autograd through the kernel forward in `torch.autograd.grad(losses.sum(), X)`
+ * (botorch/generation/gen.py:466-469).                                                         */
 int mcacq_cov_cross_bwd(int kernel_id, double outputscale, const double* U1, int64_t m1, const double* U2, int m2,
                         int d, const double* W, int64_t ldw, const double* row_scale, const double* col_vec,
                         double* dU1, int accumulate, void* stream);
 
-/* C[M x N] = A[M x K] * B[K x N], N == K == np (multiple of 16), fp64 DMMA, triangular-aware.
+/* C[M x N] = A[M x K] * B[K x N], N == K == np (multiple of 16), fp64 DMMA, triangular-aware.  Replaces
+ * `test_train_covar @ covar_cache` of gpytorch's exact_predictive_covar under fast_pred_var (the settings BoTorch
+ * applies in botorch/models/utils/assorted.py:305-315) and its transpose product in the backward pass.
  * `tile_counter` is a 4-byte device scratch word (zeroed by the call).                      */
 int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A, const double* B, double* C,
                     int32_t* tile_counter, void* stream);
