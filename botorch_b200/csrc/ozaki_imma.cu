@@ -13,17 +13,21 @@
 //
 // Kernel structure (one persistent CTA per SM, 6 warps):
 //   warp 0 / lane 0 : TMA producer.  Per 64-byte k-block it loads G A-tiles (128 rows x 64 B) and G B-tiles
-//                     (64 rows x 64 B), SWIZZLE_64B, into a ring of 12*G KB stages (3 stages at G = 6;
-//                     32-byte k-blocks with a 5-deep ring measured 25% slower).
-//   warp 1 / lane 0 : MMA issuer.  All G diagonals S_g live in TMEM at once (G x 64 columns of int32, 448 of 512),
-//                     so one k-block of operands feeds G(G+1)/2 slice products: 2.7x more tensor work per byte
-//                     staged than a pair-by-pair GEMM.  Because S_p .. S_{G-1} are adjacent TMEM column ranges,
-//                     A_p x [B_0; ..; B_{G-1-p}] is issued as ONE wide `tcgen05.mma.cta_group::1.kind::i8`
-//                     (M=128, N<=256, K=32): 10 instructions per K step at G = 7 instead of 28.
-//   warps 2-5       : epilogue.  Thread <-> TMEM lane <-> output row: `tcgen05.ld` each S_g, convert, combine in
-//                     fp64 with the diagonal weights, apply the row/column scales, store 512 contiguous bytes.
+//                     (BN rows x 64 B), SWIZZLE_64B, into a ring of G * (128 + BN) * 64 B stages (2 at G = 6 / BN = 80,
+//                     3 at G = 5 / BN = 96; 128-byte k-blocks, 7-10 % faster per byte, when two such stages fit: G <= 3).
+//   warp 1 / lane 0 : MMA issuer.  All G diagonals S_g live in TMEM at once (G x BN columns of int32; BN is the widest
+//                     multiple of 16 with G * BN <= 512), so one k-block of operands feeds G(G+1)/2 slice products.
+//                     Because S_p .. S_{G-1} are adjacent TMEM column ranges, A_p x [B_0; ..; B_{G-1-p}] is issued as
+//                     wide `tcgen05.mma.cta_group::1.kind::i8` instructions (M=128, N<=256, K=32): 9 per K step at
+//                     G = 6 instead of 21.
+//   warps 2-5       : epilogue.  Thread <-> TMEM lane <-> output row; 16 columns at a time: `tcgen05.ld` all G
+//                     diagonals, merge triples exactly in int64, convert with the 2^52+2^51 constant, combine in fp64,
+//                     apply the row/column scales, store one 128-byte line per thread.
 // Tiles are visited in an L2-friendly static order (groups of 8 row-tiles sweep the column tiles from the longest
 // k-range to the shortest); all three roles derive the same sequence from blockIdx, so no tile broadcast is needed.
+// Measured limits (profiles/r01_ozaki_int8.md): ~19-20 B/clk of operand bytes per SM and ~1.3 clk per accumulator column
+// per UMMA -- equal walls at G = 6.  Experimental variants kept behind environment switches: TMA-multicast clusters
+// (MCACQ_OZ_CLUSTER) and a cta_group::2 pair kernel (MCACQ_OZ_CTA2), both numerically identical and slower.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
