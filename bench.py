@@ -16,6 +16,7 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import torch
 
@@ -270,7 +271,28 @@ def main():
                 for _ in range(3):
                     step_round()
                 ms_round = timed(step_round, 20) / 20
-                phases = {"sweep_forward_only_points_per_s": pts_local_scale * args.steps / (ms_fwd * 1e-3),
+                opt = None
+                if world == 1:
+                    # the call a user makes: optimize_acqf over the unit box (raw-sample sweep, initial-condition selection,
+                    # batched L-BFGS-B with maxiter 50, final arg-max), wall clock of the second call
+                    import time as _time
+
+                    from botorch_b200.optim import optimize_acqf
+
+                    ob = torch.stack([torch.zeros(spec.d), torch.ones(spec.d)]).to(dev, torch.float64)
+                    okw = dict(bounds=ob, q=spec.q, num_restarts=spec.num_restarts, raw_samples=spec.raw_samples,
+                               options={"maxiter": 50, "seed": 0})
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        optimize_acqf(acqf, **okw)
+                        torch.cuda.synchronize()
+                        t0 = _time.perf_counter()
+                        _, oval = optimize_acqf(acqf, **okw)
+                        torch.cuda.synchronize()
+                        opt = {"wall_ms": (_time.perf_counter() - t0) * 1e3, "q": spec.q, "num_restarts": spec.num_restarts,
+                               "raw_samples": spec.raw_samples, "maxiter": 50, "acq_value": float(oval)}
+                phases = {"optimize_acqf": opt,
+                          "sweep_forward_only_points_per_s": pts_local_scale * args.steps / (ms_fwd * 1e-3),
                           "sweep_forward_only_ms_per_step": ms_fwd / args.steps,
                           "lbfgs_round": {"q_batches": nr, "ms_per_fwd_bwd_call": ms_round,
                                           "note": "per rank, not sharded: one optimiser round over num_restarts q-batches"}}
