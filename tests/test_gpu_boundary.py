@@ -158,3 +158,33 @@ def test_float32_callers_take_the_fused_route_in_fp64():
         vals[dt], grads[dt] = v.detach().double().cpu(), gr.double().cpu()
     assert float(((vals[torch.float32] - vals[torch.float64]).abs() / vals[torch.float64].abs()).max()) < 1e-4
     assert float((grads[torch.float32] - grads[torch.float64]).abs().max() / grads[torch.float64].abs().max()) < 1e-4
+
+
+def test_qlognei_pending_points_incremental_and_joint():
+    """qLogNEI `set_X_pending` (reference logei.py:393-459, 461-499): incremental=True folds the pending points into the
+    baseline (== an acquisition function built on cat[X_baseline, X_pending]); incremental=False appends them along q."""
+    from botorch_b200.acquisition import qLogNoisyExpectedImprovement
+    from botorch_b200.models import MaternKernel, SingleTaskGP
+    from botorch_b200.sampling import SobolQMCNormalSampler
+
+    X, Y, ls, bounds, g = _data(box=(0.0, 1.0), seed=13)
+    model = SingleTaskGP(X.to(DEV), Y.to(DEV), covar_module=MaternKernel(ard_num_dims=4, lengthscale=ls)).to(DEV)
+    model.likelihood.noise = 2e-3
+    Xb = X[:7].to(DEV)
+    P = torch.rand(2, 4, generator=g, dtype=torch.float64).to(DEV)
+    Xq = torch.rand(5, 2, 4, generator=g, dtype=torch.float64).to(DEV)
+    mk = lambda: SobolQMCNormalSampler(torch.Size([64]), seed=3)
+    inc = qLogNoisyExpectedImprovement(model, X_baseline=Xb, prune_baseline=False, sampler=mk())
+    inc.set_X_pending(P)
+    assert inc.X_pending is None and inc.X_baseline.shape[0] == 9
+    ref = qLogNoisyExpectedImprovement(model, X_baseline=torch.cat([Xb, P]), prune_baseline=False, sampler=mk())
+    with torch.no_grad():
+        assert torch.equal(inc(Xq), ref(Xq))
+        inc.set_X_pending(None)      # back to the plain baseline
+        plain = qLogNoisyExpectedImprovement(model, X_baseline=Xb, prune_baseline=False, sampler=mk())
+        assert inc.X_baseline.shape[0] == 7 and torch.equal(inc(Xq), plain(Xq))
+        joint = qLogNoisyExpectedImprovement(model, X_baseline=Xb, prune_baseline=False, sampler=mk(), incremental=False)
+        joint.set_X_pending(P)
+        assert joint.X_pending is not None and joint.X_baseline.shape[0] == 7
+        full = qLogNoisyExpectedImprovement(model, X_baseline=Xb, prune_baseline=False, sampler=mk(), incremental=False)
+        assert torch.equal(joint(Xq), full(torch.cat([Xq, P.expand(5, 2, 4)], dim=-2)))
