@@ -188,3 +188,35 @@ def test_batched_lbfgsb_drivers_agree_with_scipy_on_bound_types(driver, monkeypa
     # infeasible bounds are rejected up front
     with pytest.raises(ValueError):
         run(x0=x0, bounds=[(1.0, 0.0)] * D)
+
+
+def test_sobol_engine_cache_keeps_fresh_engines():
+    """Seeded engines are cached un-advanced (the device draw only reads their state); unseeded ones are never cached; the
+    closed form the device kernel evaluates reproduces torch's sequence (checked here in integer arithmetic on the host)."""
+    from torch.quasirandom import SobolEngine
+
+    from botorch_b200.utils.sampling import _ENGINES, _fresh_engine, draw_sobol_samples
+
+    a, b = _fresh_engine(6, 42), _fresh_engine(6, 42)
+    assert a is b and a.num_generated == 0 and (6, 42) in _ENGINES
+    assert _fresh_engine(6, None) is not _fresh_engine(6, None)
+    for i in range(40):
+        _fresh_engine(3, 1000 + i)
+    assert len(_ENGINES) <= 16
+    # host restatement of mcacq_sobol_draw: x_k = shift XOR_{b in gray(k)} sobolstate[:, b], scaled by 2^-30; row 0 is the
+    # engine's (default-dtype rounded) first point
+    eng = SobolEngine(9, scramble=True, seed=7)
+    k = torch.arange(0, 700, dtype=torch.int64)
+    gray = k ^ (k >> 1)
+    acc = eng.shift.unsqueeze(0).expand(700, -1).clone()
+    for bit in range(30):
+        m = ((gray >> bit) & 1).bool()
+        acc[m] ^= eng.sobolstate[:, bit]
+    pts = acc.to(torch.float64) * 2.0 ** -30
+    pts[0] = eng._first_point.to(torch.float64).reshape(-1)
+    assert torch.equal(pts, SobolEngine(9, scramble=True, seed=7).draw(700, dtype=torch.float64))
+    # CPU bounds keep the reference's host path
+    bounds = torch.tensor([[0.0, -1.0], [2.0, 1.0]], dtype=torch.float64)
+    x = draw_sobol_samples(bounds=bounds, n=16, q=3, seed=5)
+    ref = SobolEngine(6, scramble=True, seed=5).draw(16, dtype=torch.float64).view(16, 3, 2) * (bounds[1] - bounds[0]) + bounds[0]
+    assert torch.equal(x, ref)
