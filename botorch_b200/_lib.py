@@ -67,7 +67,7 @@ EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
-    "mcacq_ozaki_contract", "mcacq_cov_cross_sliced",
+    "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
 ]
 
 
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.mcacq_ozaki_contract.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
     L.mcacq_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     L.mcacq_workspace_bytes.restype = sz
+    L.mcacq_workspace_bytes_model.argtypes = [C.POINTER(Model), i64, i32, i32]
+    L.mcacq_workspace_bytes_model.restype = sz
     L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]
     L.mcacq_posterior_backward.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, vp, sz, vp]
     L.mcacq_acq_forward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, sz, vp]
@@ -105,7 +107,7 @@ def lib() -> C.CDLL:
     L.mcacq_log_areas_backward.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mcacq_version", "mcacq_workspace_bytes"):
+        if name not in ("mcacq_version", "mcacq_workspace_bytes", "mcacq_workspace_bytes_model"):
             fn.restype = i32
     _lib = L
     return L

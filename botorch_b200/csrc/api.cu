@@ -45,7 +45,9 @@ struct Workspace {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int int8_mode = 1) {
+// int8_g: 0 = FP64 DMMA contraction (no slice buffers), otherwise the number of int8 slices of the M x np left operand
+// (max of the forward and backward diagonals of the model).
+static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int int8_g) {
   Workspace w;
   char* p = (char*)base;
   size_t off = 0;
@@ -72,10 +74,15 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int i
   // operands of the optional INT8 contraction: 6 slices of the M x np left operand + its row scales
   w.slice_scale = (double*)take((size_t)M * 8);
   w.A_absmax = (double*)take((size_t)M * 8);
-  w.mean_part = (double*)take(int8_mode ? (size_t)((np + 63) / 64) * M * 8 : 256);
-  w.slices = (int8_t*)take(int8_mode ? (size_t)6 * M * np : 256);
+  w.mean_part = (double*)take(int8_g ? (size_t)((np + 63) / 64) * M * 8 : 256);
+  w.slices = (int8_t*)take(int8_g ? (size_t)int8_g * M * np : 256);
   w.bytes = off;
   return w;
+}
+
+static inline int model_int8_g(const mcacq_model* m) {
+  if (m->contraction != 1) return 0;
+  return m->g_fwd > m->g_bwd ? m->g_fwd : m->g_bwd;
 }
 
 static int check_model(const mcacq_model* m) {
@@ -87,7 +94,7 @@ static int check_model(const mcacq_model* m) {
   if (m->contraction != 0 && m->contraction != 1) return MCACQ_EINVAL;
   if (m->contraction == 1) {
     if (!m->Rt_slices || !m->Rt_scale || !m->R_slices || !m->R_scale) return MCACQ_EINVAL;
-    if (m->g_fwd < 1 || m->g_fwd > 6 || m->g_bwd < 1 || m->g_bwd > 6) return MCACQ_EINVAL;
+    if (m->g_fwd < 1 || m->g_fwd > MCACQ_MAX_SLICES || m->g_bwd < 1 || m->g_bwd > MCACQ_MAX_SLICES) return MCACQ_EINVAL;
   }
   return 0;
 }
@@ -147,7 +154,12 @@ extern "C" int mcacq_last_launch_count(void) { return g_launch_count; }
 
 extern "C" size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r) {
   if (b < 0 || q <= 0 || d <= 0 || np <= 0 || r < 0) return 0;
-  return carve(nullptr, b, q, d, np, r).bytes;
+  return carve(nullptr, b, q, d, np, r, MCACQ_MAX_SLICES).bytes;  // worst case over the contraction modes
+}
+
+extern "C" size_t mcacq_workspace_bytes_model(const mcacq_model* model, int64_t b, int q, int r) {
+  if (check_model(model) != 0 || b < 0 || q <= 0 || r < 0) return 0;
+  return carve(nullptr, b, q, model->d, model->np, r, model_int8_g(model)).bytes;
 }
 
 extern "C" int mcacq_posterior(const mcacq_model* model, const double* X, int64_t b, int q, double* mean,
@@ -160,7 +172,7 @@ extern "C" int mcacq_posterior(const mcacq_model* model, const double* X, int64_
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
-  Workspace w = carve(workspace, b, q, model->d, model->np, 0);
+  Workspace w = carve(workspace, b, q, model->d, model->np, 0, model_int8_g(model));
   if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
   // write mean / covariance straight into the caller's buffers
   w.mean = mean;
@@ -217,7 +229,7 @@ extern "C" int mcacq_posterior_backward(const mcacq_model* model, const double* 
   if (q > MCACQ_MAX_Q) return MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
-  Workspace w = carve(workspace, b, q, model->d, model->np, 0);
+  Workspace w = carve(workspace, b, q, model->d, model->np, 0, model_int8_g(model));
   if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
   return run_posterior_backward(model, nullptr, b, q, gmean, gcovar, nullptr, w, grad_X, (cudaStream_t)stream);
 }
@@ -257,7 +269,7 @@ extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline*
   if (r > MCACQ_MAX_R) return MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
-  Workspace w = carve(workspace, b, q, model->d, model->np, r);
+  Workspace w = carve(workspace, b, q, model->d, model->np, r, model_int8_g(model));
   if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = run_posterior_stage(model, base, X, b, q, w, st))) return rc;
@@ -281,7 +293,7 @@ extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline
   if (r < 0 || r > MCACQ_MAX_R) return r < 0 ? MCACQ_EINVAL : MCACQ_ELIMIT;
   if (b == 0) return 0;
   g_launch_count = 0;
-  Workspace w = carve(workspace, b, q, model->d, model->np, r);
+  Workspace w = carve(workspace, b, q, model->d, model->np, r, model_int8_g(model));
   if (w.bytes > workspace_bytes) return MCACQ_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   SRParams sp;

@@ -47,7 +47,7 @@ __device__ __forceinline__ double kernel_dfactor(int kernel_id, double outputsca
 // X (|X| <= 2^(8G-2)) = sum_i d_i 256^i with d_i in [-128, 127].  Adding 128 to every byte position turns the carry
 // chain into ONE 64-bit addition: the bytes of Y = X + 0x80..80 are d_i + 128, i.e. d_i = byte_i(Y) ^ 0x80 as int8.
 __device__ __forceinline__ unsigned long long balanced_bytes(long long X) {
-  return ((unsigned long long)X + 0x0000808080808080ull) ^ 0x0000808080808080ull;
+  return ((unsigned long long)X + 0x0080808080808080ull) ^ 0x0080808080808080ull;
 }
 // byte `i` (0 = least significant digit) of four packed values -> one 32-bit word (4 consecutive int8 outputs)
 __device__ __forceinline__ unsigned pack_digit4(const unsigned long long (&Y)[4], int i) {

@@ -392,7 +392,7 @@ extern "C" int mcacq_cov_cross_sliced(int kernel_id, double outputscale, const d
                                       int8_t* slices, double* mean_part, void* stream) {
   if (!U1 || !U2 || !alpha || !slices || !mean_part || m1 < 0 || m2 < 0 || d <= 0 || ldk < m2 || (ldk % 16) != 0)
     return MCACQ_EINVAL;
-  if (G < 1 || G > 6) return MCACQ_EINVAL;
+  if (G < 1 || G > 7) return MCACQ_EINVAL;
   return mcacq::cov_cross_launch(true, kernel_id, outputscale, U1, m1, U2, m2, d, nullptr, ldk, slices, G, fixed_exp, alpha,
                                  mean_part, (cudaStream_t)stream);
 }

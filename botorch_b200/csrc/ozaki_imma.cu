@@ -39,7 +39,7 @@ constexpr int OZ_MAX_BN = 256;           // the column-tile width BN is a templa
                                          // TMEM columns (G = 6: 80, G = 5: 96, G = 4: 128), because the operand bytes an SM has to
                                          // ingest per MAC fall as BM * BN / (BM + BN)
 constexpr int OZ_MAX_STAGES = 4;                    // ring depth is chosen at run time: as many 12*G KB stages as fit
-constexpr int OZ_MAXG = 6;
+constexpr int OZ_MAXG = 7;
 constexpr int OZ_GROUP_M = 8;
 constexpr int OZ_THREADS = 192;
 
@@ -128,9 +128,13 @@ __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles,
 
 template <int OZ_BK, int OZ_BN, int CM, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int tri_mode,
+ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapC, int tri_mode,
                   int64_t M, int N, int K, int G, int stages, const double* __restrict__ row_scale,
-                  const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc, int l2_hints, int group_m) {
+                  const double* __restrict__ col_scale, double* __restrict__ C, int64_t ldc, int l2_hints, int group_m, int dbg,
+                  int tma_store) {
+  // dbg (developer switches, MCACQ_OZ_DEBUG): bit 0 = do not issue the UMMAs (pure TMA ingest rate), bit 1 = do not issue
+  // the TMA loads (pure MMA + epilogue rate on stale shared memory), bit 2 = one TMA box per operand spanning all G slices.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
@@ -183,9 +187,14 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
           const int s = (int)(it % stages);
           if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
+          if (dbg & 2) { oz_mbar_arrive(&full_bar[s]); continue; }
           oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + (size_t)s * stage_bytes;
-          if (CSIZE == 1 && l2_hints) {
+          if (CSIZE == 1 && (dbg & 4)) {
+            // the maps were encoded with a box depth of G slices: the slice-major stage layout is the same
+            oz_tma_3d(st, &mapA, &full_bar[s], kb * OZ_BK, row0, 0);
+            oz_tma_3d_hint(st + G * OZ_A_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, 0, pol_keep);
+          } else if (CSIZE == 1 && l2_hints) {
             // the B slices (the triangular factor, re-used by every row tile of the launch) are kept in L2 with
             // evict_last; the A slices are only re-used by the column tiles of the current row group
             for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
@@ -225,6 +234,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           // the A tile is read from shared memory once per p, not once per pair.
 #pragma unroll
           for (int k = 0; k < OZ_BK / 32; k++) {
+            if (dbg & 1) break;
             for (int p = 0; p < G; p++) {
               const uint64_t ad = oz_desc<OZ_BK>(st + p * OZ_A_TILE) + 2 * k;
               const int ncols = (G - p) * OZ_BN;
@@ -249,6 +259,10 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int etid = tid - 64;                // 0..127
     int64_t tile_i = 0;
     OzTile tl;
+    // output staging: 2 x 4 KB (32 rows x 128 B, SWIZZLE_128B) per epilogue warp, behind the operand ring
+    uint8_t* epi_stage = smem + (size_t)stages * stage_bytes;
+    epi_stage = (uint8_t*)(((uintptr_t)epi_stage + 1023) & ~(uintptr_t)1023);
+    uint32_t epi_chunk = 0;
     for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
       const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
       const int col0 = (tl.nt * CN + rn) * OZ_BN;
@@ -265,7 +279,10 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       double* dst = C + (row_ok ? row : 0) * ldc + col0;
       const bool vec_ok = (ldc & 1) == 0;
       // 16 output columns at a time: all G diagonals of the chunk are fetched from TMEM, combined in fp64 with the
-      // weights 256^-(g+2), scaled and stored (one 128-byte line per thread and chunk)
+      // weights 256^-(g+2) and scaled.  Output: the warp's 32 rows x 16 columns are staged in shared memory in the
+      // SWIZZLE_128B layout (conflict-free 16-byte stores) and written by ONE TMA store per chunk, i.e. as full 128-byte
+      // lines -- a thread-per-row store pattern hits 32 different lines per instruction with half-filled sectors and made
+      // the epilogue (which cannot overlap the main loop: all 512 TMEM columns hold accumulators) 23 % of the kernel.
 #pragma unroll 1
       for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
         double acc[16];
@@ -295,8 +312,8 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 const long long s0 = (long long)(int32_t)v[g0][j];
-                const long long s1 = (g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1][j] : 0ll;
-                const long long s2 = (g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2][j] : 0ll;
+                const long long s1 = (g0 + 1 < OZ_MAXG && g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1 < OZ_MAXG ? g0 + 1 : g0][j] : 0ll;
+                const long long s2 = (g0 + 2 < OZ_MAXG && g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2 < OZ_MAXG ? g0 + 2 : g0][j] : 0ll;
                 const long long t = s0 * 65536ll + s1 * 256ll + s2;
                 const double d = __longlong_as_double(0x4338000000000000ll + t) - 6755399441055744.0;
                 acc[j] = fma(w, d, acc[j]);
@@ -305,7 +322,27 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
           }
         }
-        if (row_ok && col0 + c0 < N) {
+        if (tma_store) {
+          if (col0 + c0 < N) {   // warp-uniform
+            uint8_t* sbuf = epi_stage + (size_t)((lg * 2 + (epi_chunk & 1)) * 4096);
+            // the store issued two chunks ago read from this buffer: it must have finished reading before we overwrite
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+              *reinterpret_cast<double2*>(sbuf + lane * 128 + ((((j >> 1) ^ (lane & 7))) << 4)) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&mapC), "r"(oz_smem_u32(sbuf)), "r"(col0 + c0), "r"((int)((tl.mt * CM + rm) * OZ_BM + lg * 32)) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            epi_chunk++;
+          }
+        } else if (row_ok && col0 + c0 < N) {
           if (col0 + c0 + 16 <= N && vec_ok) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -325,6 +362,7 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       if (lane == 0) oz_mbar_arrive(&acc_empty);
       asm volatile("bar.sync 1, 128;" ::: "memory");  // s_col reuse
     }
+    if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -497,8 +535,8 @@ ozaki_imma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 const long long s0 = (long long)(int32_t)v[g0][j];
-                const long long s1 = (g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1][j] : 0ll;
-                const long long s2 = (g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2][j] : 0ll;
+                const long long s1 = (g0 + 1 < OZ_MAXG && g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1 < OZ_MAXG ? g0 + 1 : g0][j] : 0ll;
+                const long long s2 = (g0 + 2 < OZ_MAXG && g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2 < OZ_MAXG ? g0 + 2 : g0][j] : 0ll;
                 const long long tt = s0 * 65536ll + s1 * 256ll + s2;
                 const double dd = __longlong_as_double(0x4338000000000000ll + tt) - 6755399441055744.0;
                 acc[j] = fma(w, dd, acc[j]);
@@ -596,12 +634,12 @@ static OzEncodeFn oz_encode_fn() {
 }
 
 static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_t rows, uint64_t kbytes, uint64_t pitch,
-                       uint32_t box_rows, int OZ_BK) {
+                       uint32_t box_rows, int OZ_BK, uint32_t box_slices = 1) {
   OzEncodeFn enc = oz_encode_fn();
   if (!enc) return MCACQ_EINVAL;
   cuuint64_t dims[3] = {kbytes, rows, slices};
   cuuint64_t strides[2] = {pitch, pitch * rows};
-  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, box_rows, box_slices};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, OZ_BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -610,10 +648,24 @@ static int oz_make_map(CUtensorMap* m, const void* ptr, uint64_t slices, uint64_
   return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
 }
 
+static int oz_make_map_c(CUtensorMap* m, const double* C, uint64_t rows, uint64_t cols, uint64_t ldc) {
+  OzEncodeFn enc = oz_encode_fn();
+  if (!enc) return MCACQ_EINVAL;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ldc * 8};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(C), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCACQ_EINVAL;
+}
+
 template <int BKB, int OZ_BN, int CM, int CN>
-static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M, int N, int K, int G,
+static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC, int tma_store, int tri_mode,
+                       int64_t M, int N, int K, int G,
                        int stages, size_t smem, size_t smem_budget, const double* row_scale, const double* col_scale,
-                       double* C, int64_t ldc, cudaStream_t st) {
+                       double* C, int64_t ldc, cudaStream_t st, int dbg) {
   auto kern = ozaki_imma_kernel<BKB, OZ_BN, CM, CN>;
   static int max_clusters = -1;
   constexpr int CS = CM * CN;
@@ -649,7 +701,8 @@ static int oz_launch_t(const CUtensorMap& mapA, const CUtensorMap& mapB, int tri
   const int64_t ctiles = ((m_tiles + CM - 1) / CM) * ((n_tiles + CN - 1) / CN);
   const int nclusters = (int)(ctiles < max_clusters ? ctiles : max_clusters);
   cfg.gridDim = dim3(nclusters * CS);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc, l2_hints, group_m);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapC, tri_mode, M, N, K, G, stages, row_scale, col_scale, C, ldc, l2_hints, group_m, dbg,
+                                     tma_store);
   count_launch();
   if (e != cudaSuccess) return (int)e;
   MCACQ_CUDA_CHECK_LAUNCH();
@@ -696,11 +749,12 @@ static int oz_launch2_t(const CUtensorMap& mapA, const CUtensorMap& mapBh, int t
   return 0;
 }
 
-static int oz_launch(int bk, int bn, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, int tri_mode, int64_t M,
+static int oz_launch(int bk, int bn, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
+                     int tma_store, int tri_mode, int64_t M,
                      int N, int K, int G, int stages, size_t smem, size_t smem_budget, const double* row_scale,
-                     const double* col_scale, double* C, int64_t ldc, cudaStream_t st) {
+                     const double* col_scale, double* C, int64_t ldc, cudaStream_t st, int dbg) {
 #define OZ_CASE(B, W, A_, C_) if (bk == B && bn == W && cm == A_ && cn == C_) \
-    return oz_launch_t<B, W, A_, C_>(mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc, st);
+    return oz_launch_t<B, W, A_, C_>(mapA, mapB, mapC, tma_store, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc, st, dbg);
   OZ_CASE(64, 64, 1, 1) OZ_CASE(64, 80, 1, 1) OZ_CASE(64, 96, 1, 1) OZ_CASE(64, 128, 1, 1) OZ_CASE(64, 160, 1, 1) OZ_CASE(64, 256, 1, 1)
   OZ_CASE(128, 64, 1, 1) OZ_CASE(128, 128, 1, 1) OZ_CASE(128, 160, 1, 1) OZ_CASE(128, 256, 1, 1)
   // cluster (TMA multicast) variants, kept for the record: measured equal or slower (profiles/r01_ozaki_int8.md)
@@ -744,12 +798,15 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   int bn = (getenv("MCACQ_OZ_BN") != nullptr) ? atoi(getenv("MCACQ_OZ_BN")) : oz_pick_bn(G);
   if (bn < 16 || bn > OZ_MAX_BN || (bn % 16) != 0 || G * bn > 512) return MCACQ_EINVAL;
   int bk = (getenv("MCACQ_OZ_BK") != nullptr) ? atoi(getenv("MCACQ_OZ_BK")) : 0;
-  if (bk != 64 && bk != 128) bk = (bn != 80 && bn != 96 && (size_t)2 * G * (OZ_BM + bn) * 128 <= smem_budget) ? 128 : 64;
+  // the epilogue stages its output for TMA stores: 4 warps x 2 buffers x 4 KB (+ 1 KB alignment) behind the operand ring
+  const size_t epi_bytes = 4 * 2 * 4096 + 1024;
+  if (bk != 64 && bk != 128) bk = (bn != 80 && bn != 96 && (size_t)2 * G * (OZ_BM + bn) * 128 <= smem_budget - epi_bytes) ? 128 : 64;
   const size_t stage_bytes = (size_t)G * (OZ_BM + bn) * bk;
-  int stages = (int)(smem_budget / stage_bytes);
+  int stages = (int)((smem_budget - epi_bytes) / stage_bytes);
   if (stages > OZ_MAX_STAGES) stages = OZ_MAX_STAGES;
+  if (getenv("MCACQ_OZ_STAGES") != nullptr) { int v = atoi(getenv("MCACQ_OZ_STAGES")); if (v >= 1 && v < stages) stages = v; }
   if (stages < 1) return MCACQ_ELIMIT;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + epi_bytes;
   const int cta2 = (getenv("MCACQ_OZ_CTA2") != nullptr) ? atoi(getenv("MCACQ_OZ_CTA2")) : 0;
   if (cta2 && (bn == 64 || bn == 80 || bn == 96 || bn == 128)) {
     // CTA-pair variant: 64-byte k-blocks, half B tiles per CTA
@@ -770,14 +827,23 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   }
   CUtensorMap mapA, mapB;
   int rc;
-  if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk))) return rc;
-  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, bk))) return rc;
+  const int dbg = (getenv("MCACQ_OZ_DEBUG") != nullptr) ? atoi(getenv("MCACQ_OZ_DEBUG")) : 0;
+  const uint32_t box_slices = (dbg & 4) ? (uint32_t)G : 1u;
+  if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk, box_slices))) return rc;
+  if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, bk, box_slices))) return rc;
   // Cluster shape (rows x columns of CTA tiles sharing operand loads through TMA multicast).  Measured on B200
   // (profiles/r01_ozaki_int8.md): multicast halves the L2 reads but not the bytes delivered to each SM, which is what
   // bounds this kernel (~20 B/clk/SM, ~5.8 TB/s chip-wide), so 1x1 is the default; 2x1 / 1x2 tie, 2x2 is 13% slower.
   int cm = 1, cn = 1;
   if (getenv("MCACQ_OZ_CLUSTER") != nullptr) { int v = atoi(getenv("MCACQ_OZ_CLUSTER")); cm = v / 10; cn = v % 10; }
   if (cm * cn > 1 && (bn != 64 || bk != 64)) return MCACQ_EINVAL;
-  return oz_launch(bk, bn, cm, cn, mapA, mapB, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
-                   (cudaStream_t)stream);
+  if (cm * cn > 1 && (dbg & 4)) return MCACQ_EINVAL;
+  // output map (fp64, 16 x 32 boxes, SWIZZLE_128B); TMA needs a 16-byte aligned base and row pitch, otherwise the
+  // epilogue falls back to per-thread stores
+  CUtensorMap mapC = mapA;
+  int tma_store = ((ldc & 1) == 0 && ((uintptr_t)C & 15) == 0) ? 1 : 0;
+  if (getenv("MCACQ_OZ_TMASTORE") != nullptr) tma_store = tma_store && atoi(getenv("MCACQ_OZ_TMASTORE"));
+  if (tma_store && oz_make_map_c(&mapC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc) != 0) tma_store = 0;
+  return oz_launch(bk, bn, cm, cn, mapA, mapB, mapC, tma_store, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
+                   (cudaStream_t)stream, dbg);
 }

@@ -136,7 +136,7 @@ class SingleTaskGP(Model):
         # the tensors are kept alive next to the cached strategy (`_strategy_tensors`), so neither their Python identity nor
         # their storage address can be recycled by a replacement tensor while the key is in use
         self._key_tensors = tensors
-        return (self.train_inputs[0].device, settings.contraction.value(), ident)
+        return (self.train_inputs[0].device, settings.contraction.value(), settings.int8_slices.value(), ident)
 
     def _base_kernel(self) -> Kernel:
         k = self.covar_module.base_kernel if isinstance(self.covar_module, ScaleKernel) else self.covar_module
@@ -208,7 +208,9 @@ class SingleTaskGP(Model):
         if isinstance(observation_noise, Tensor) or observation_noise:
             s2 = strat.y_std**2
             if isinstance(observation_noise, Tensor):
-                covar = covar + torch.diag_embed(observation_noise.reshape(*covar.shape[:-1]).to(covar))
+                # the reference adds the tensor through the likelihood BEFORE `untransform_posterior`
+                # (models/gpytorch.py:517-527, 603-605), i.e. it is noise on the standardised scale
+                covar = covar + s2 * torch.diag_embed(observation_noise.reshape(*covar.shape[:-1]).to(covar))
             else:
                 covar = covar + torch.diag_embed((self.likelihood.noise.mean() * s2).expand(covar.shape[:-1]).to(covar))
         mean = mean.reshape(*batch_shape, q)

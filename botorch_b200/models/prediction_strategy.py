@@ -15,7 +15,7 @@ import warnings
 import torch
 from torch import Tensor
 
-from .. import _lib
+from .. import _lib, settings
 from ..exceptions.errors import NanError, NotPSDError
 from ..exceptions.warnings import NumericalWarning
 
@@ -104,66 +104,117 @@ class DevicePredictionStrategy:
         self.Rt[:n, :n] = Linv
         del Linv
         self.train_chol = chol
-        # optional INT8 tensor-core contraction: signed 8-bit row-scaled slices of R^T (forward) and R (backward)
+        # INT8 tensor-core contraction: signed 8-bit row-scaled slices of R^T (forward) and R (backward)
         self.contraction = contraction
         if contraction not in ("dmma", "int8"):
             raise ValueError("contraction must be 'dmma' or 'int8'")
         self.Rt_slices = self.Rt_scale = self.R_slices = self.R_scale = None
-        if contraction == "int8":
-            self.Rt_slices, self.Rt_scale = self._slice_rows(self.Rt)
-            self.R_slices, self.R_scale = self._slice_rows(self.R)
+        self.g_fwd, self.g_bwd = self.G_FWD_LADDER[0], self.G_BWD_LADDER[0]
         self.desc = _lib.Model(
             n=n, d=d, np=npad, kernel_id=kernel_id, outputscale=self.outputscale, mean_const=self.mean_const,
             y_mean=self.y_mean, y_std=self.y_std, x_offset=self.x_offset.data_ptr(), x_coef=self.x_coef.data_ptr(),
             lengthscale=self.lengthscale.data_ptr(), U_train=self.U_train.data_ptr(), alpha=self.alpha.data_ptr(),
             R=self.R.data_ptr(), Rt=self.Rt.data_ptr(),
-            contraction=1 if contraction == "int8" else 0, g_fwd=6, g_bwd=5, _pad=0,
-            Rt_slices=_lib.ptr(self.Rt_slices), Rt_scale=_lib.ptr(self.Rt_scale),
-            R_slices=_lib.ptr(self.R_slices), R_scale=_lib.ptr(self.R_scale),
+            contraction=0, g_fwd=self.g_fwd, g_bwd=self.g_bwd, _pad=0,
+            Rt_slices=None, Rt_scale=None, R_slices=None, R_scale=None,
         )
-
+        self.int8_probe_error = self.int8_probe_grad_error = None
         if contraction == "int8":
-            self._guard_int8(Xt)
+            self._select_int8(Xt)
 
-    # The slices are FIXED-point relative to each row's largest entry: the int8 contraction reproduces the posterior
-    # variance to ~1e-12 of the PRIOR variance (measured 3e-13 .. 9e-13 on C1-C3), i.e. to 1e-8 .. 1e-11 of the variance
-    # itself depending on how far it has collapsed (1.2e-8 AT the C3 training points, 5e-11 in the rest of the box).
-    # When K is so ill-conditioned that the variance collapses by more than ~5 orders of magnitude everywhere, the digits
-    # the fp64 contraction keeps are lost: the probe below detects that and switches the model to 'dmma'.
-    INT8_PROBE_TOL = 1e-7
-    INT8_PROBE_GRAD_TOL = 1e-6   # gradient of the probe variances (C1-C3 measure ~1e-8)
+    # The slices are FIXED-point relative to each row's largest entry, so the int8 contraction reproduces the posterior
+    # variance to ~2^-(8G-2) of the PRIOR variance, not of the variance itself: with G = 6 that is ~1e-12 of the prior
+    # (5e-11 of the variance over the search box, 1.2e-8 exactly AT the C3 training points, where it has collapsed by four
+    # orders of magnitude); every extra slice buys 2^-8.  `_select_int8` therefore measures, per fitted model, the
+    # variance and gradient error of the int8 path against the FP64 contraction on a probe set built around the training
+    # points (the worst cancellation) and picks the SMALLEST number of slices that keeps the north-star bars
+    # (variance 1e-9 pointwise, gradients 1e-7) with a 2x-4x margin; a model no ladder entry serves runs on 'dmma'.
+    G_FWD_LADDER = (6, 7)
+    G_BWD_LADDER = (5, 6, 7)
+    INT8_PROBE_TOL = 2.5e-10
+    INT8_PROBE_GRAD_TOL = 2.5e-8
 
-    def _guard_int8(self, Xt: Tensor) -> None:
-        """Probe the int8 contraction against the FP64 one on this model (training points: smallest posterior variances,
-        hence the worst cancellation; plus uniform points of their bounding box) and fall back to 'dmma' when the
-        posterior variance differs by more than INT8_PROBE_TOL (relative, pointwise)."""
+    def _probe_points(self, Xt: Tensor) -> Tensor:
+        """Training points (smallest posterior variances, hence the worst cancellation), the same points displaced by
+        1e-6 and 1e-3 of the bounding box, and uniform points of the box -- in the raw input space, P x 1 x d."""
         n = Xt.shape[0]
-        take = torch.linspace(0, n - 1, min(n, 256), device=Xt.device).round().long()
+        take = torch.linspace(0, n - 1, min(n, 192), device=Xt.device).round().long()
         g = torch.Generator(device="cpu").manual_seed(0)
         lo, hi = Xt.min(dim=0).values, Xt.max(dim=0).values
-        box = lo + (hi - lo) * torch.rand(256, self.d, generator=g, dtype=torch.float64).to(Xt.device)
-        probe = torch.cat([Xt[take], box]) * self.x_coef + self.x_offset  # back to the raw input space
-        probe = probe.unsqueeze(1)  # P x 1 x d
-        v8, g8 = self._probe_variance_and_grad(probe)
+        width = (hi - lo).clamp_min(1e-12)
+        T = Xt[take]
+        dirs = torch.randn(T.shape[0], self.d, generator=g, dtype=torch.float64).to(Xt.device)
+        dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+        box = lo + width * torch.rand(256, self.d, generator=g, dtype=torch.float64).to(Xt.device)
+        pts = torch.cat([T, T + 1e-6 * width * dirs, T + 1e-3 * width * dirs, box])
+        return (pts * self.x_coef + self.x_offset).unsqueeze(1)
+
+    def _set_slices(self, g_fwd: int, g_bwd: int) -> None:
+        if self.Rt_slices is None or self.Rt_slices.shape[0] != g_fwd:
+            self.Rt_slices, self.Rt_scale = self._slice_rows(self.Rt, g_fwd)
+        if self.R_slices is None or self.R_slices.shape[0] != g_bwd:
+            self.R_slices, self.R_scale = self._slice_rows(self.R, g_bwd)
+        self.g_fwd, self.g_bwd = g_fwd, g_bwd
+        self.desc.g_fwd, self.desc.g_bwd = g_fwd, g_bwd
+        self.desc.Rt_slices, self.desc.Rt_scale = self.Rt_slices.data_ptr(), self.Rt_scale.data_ptr()
+        self.desc.R_slices, self.desc.R_scale = self.R_slices.data_ptr(), self.R_scale.data_ptr()
+        self.desc.contraction = 1
+
+    def _int8_exact(self, g: int) -> bool:
+        # every diagonal of slice products must stay exact in int32 (ozaki_imma.cu: K * 128^2 * G < 2^31)
+        return self.np * 16384 * g < 2**31
+
+    def _select_int8(self, Xt: Tensor) -> None:
+        """Pick (g_fwd, g_bwd) for this model, or fall back to 'dmma' (see the comment above)."""
+        forced = settings.int8_slices.value()
+        if forced is not None:  # developer / benchmark override: fixed slice counts, no probe
+            if not (self._int8_exact(max(forced))):
+                raise _lib.McacqError("settings.int8_slices: train set too large for exact int32 slice products")
+            self._set_slices(int(forced[0]), int(forced[1]))
+            return
+        probe = self._probe_points(Xt)
         self.desc.contraction = 0
         v64, g64 = self._probe_variance_and_grad(probe)
         floor = 1e-8 * self.y_std * self.y_std * self.outputscale
-        err = float(((v8 - v64).abs() / v64.abs().clamp_min(floor)).max())
-        gerr = float((g8 - g64).abs().max() / g64.abs().max().clamp_min(1e-300))
+        gmax = g64.abs().max().clamp_min(1e-300)
+        chosen_f = None
+        err = gerr = float("inf")
+        for gf in self.G_FWD_LADDER:
+            if not self._int8_exact(gf):
+                break
+            self._set_slices(gf, self.G_BWD_LADDER[0])
+            v8, _ = self._probe_variance_and_grad(probe, backward=False)
+            err = float(((v8 - v64).abs() / v64.abs().clamp_min(floor)).max())
+            if err <= self.INT8_PROBE_TOL:
+                chosen_f = gf
+                break
+        chosen_b = None
+        if chosen_f is not None:
+            for gb in self.G_BWD_LADDER:
+                if not self._int8_exact(gb):
+                    break
+                self._set_slices(chosen_f, gb)
+                _, g8 = self._probe_variance_and_grad(probe)
+                gerr = float((g8 - g64).abs().max() / gmax)
+                if gerr <= self.INT8_PROBE_GRAD_TOL:
+                    chosen_b = gb
+                    break
         self.int8_probe_error, self.int8_probe_grad_error = err, gerr
-        if err <= self.INT8_PROBE_TOL and gerr <= self.INT8_PROBE_GRAD_TOL:
-            self.desc.contraction = 1
+        if chosen_f is not None and chosen_b is not None:
+            self._set_slices(chosen_f, chosen_b)
             return
-        warnings.warn(f"int8 contraction disabled for this model: on the probe set the posterior variance differs by {err:.1e} "
-                      f"and its gradient by {gerr:.1e} (relative) from the FP64 contraction (ill-conditioned train "
-                      "covariance); using 'dmma'.", NumericalWarning, stacklevel=3)
+        why = ("train set too large for exact int32 slice products" if not self._int8_exact(self.G_FWD_LADDER[0]) else
+               f"on the probe set the posterior variance differs by {err:.1e} and its gradient by {gerr:.1e} (relative) from "
+               "the FP64 contraction (ill-conditioned train covariance)")
+        warnings.warn(f"int8 contraction disabled for this model: {why}; using 'dmma'.", NumericalWarning, stacklevel=3)
         self.contraction = "dmma"
         self.Rt_slices = self.Rt_scale = self.R_slices = self.R_scale = None
+        self.desc.contraction = 0
         self.desc.Rt_slices = self.desc.Rt_scale = self.desc.R_slices = self.desc.R_scale = None
 
-    def _probe_variance_and_grad(self, probe: Tensor) -> tuple[Tensor, Tensor]:
+    def _probe_variance_and_grad(self, probe: Tensor, backward: bool = True) -> tuple[Tensor, Tensor | None]:
         """Posterior variance at P single points and d(sum of variances)/dX through the forward AND backward contraction of
-        the current mode (the backward one uses one slice less, so it is the first to lose digits)."""
+        the current mode (the backward one uses fewer slices, so it is the first to lose digits)."""
         P = probe.shape[0]
         L, st = _lib.lib(), _lib.stream_ptr()
         f64 = dict(device=self.device, dtype=torch.float64)
@@ -172,12 +223,14 @@ class DevicePredictionStrategy:
         ws = self.workspace(P, 1, 0)
         _lib.check(L.mcacq_posterior(C.byref(self.desc), X.data_ptr(), P, 1, mean.data_ptr(), covar.data_ptr(), ws.data_ptr(),
                                      ws.numel(), st), "mcacq_posterior (probe)")
+        if not backward:
+            return covar.reshape(-1), None
         gm, gc = torch.zeros(P, 1, **f64), torch.ones(P, 1, 1, **f64)
         _lib.check(L.mcacq_posterior_backward(C.byref(self.desc), X.data_ptr(), P, 1, gm.data_ptr(), gc.data_ptr(),
                                               gX.data_ptr(), ws.data_ptr(), ws.numel(), st), "mcacq_posterior_backward (probe)")
         return covar.reshape(-1), gX.reshape(P, self.d)
 
-    def _slice_rows(self, Mx: Tensor, G: int = 6) -> tuple[Tensor, Tensor]:
+    def _slice_rows(self, Mx: Tensor, G: int) -> tuple[Tensor, Tensor]:
         rows, K = Mx.shape
         S = torch.empty(G, rows, K, dtype=torch.int8, device=self.device)
         scale = torch.empty(rows, dtype=torch.float64, device=self.device)
@@ -187,7 +240,9 @@ class DevicePredictionStrategy:
 
     # ---------------------------------------------------------------- helpers over the C ABI
     def workspace(self, b: int, q: int, r: int = 0) -> Tensor:
-        nbytes = _lib.lib().mcacq_workspace_bytes(b, q, self.d, self.np, r)
+        nbytes = _lib.lib().mcacq_workspace_bytes_model(C.byref(self.desc), b, q, r)
+        if nbytes == 0 and b > 0:
+            raise _lib.McacqError("mcacq_workspace_bytes_model: invalid model descriptor or shape")
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def scale(self, X: Tensor) -> Tensor:

@@ -29,3 +29,31 @@ def columnwise_clamp(X: Tensor, lower=None, upper=None, raise_on_violation: bool
 
 def _arrayify(X: Tensor) -> np.ndarray:
     return X.cpu().detach().contiguous().double().clone().numpy()
+
+
+def get_X_baseline(acq_function) -> Tensor | None:
+    """The acquisition function's `X_baseline`, else the model's (untransformed) training inputs
+    (reference optim/utils/acquisition_utils.py:129-170)."""
+    import warnings
+
+    from ..exceptions.warnings import BotorchWarning
+
+    try:
+        X = acq_function.X_baseline
+        if X.shape[0] == 0:
+            raise BotorchError
+    except (BotorchError, AttributeError):
+        try:
+            model = acq_function.model
+        except AttributeError:
+            warnings.warn("Failed to extract X_baseline.", BotorchWarning)
+            return None
+        try:
+            m = model.models[0] if hasattr(model, "models") else model
+            X = m.train_X_raw if hasattr(m, "train_X_raw") else m.train_inputs[0]
+        except (BotorchError, AttributeError, IndexError):
+            warnings.warn("Failed to extract X_baseline.", BotorchWarning)
+            return None
+    while X.ndim > 2:
+        X = X[0]
+    return X

@@ -3,8 +3,12 @@
 `contraction` selects how the dominant contraction `K(X, X_train) @ L^{-T}` (and its transpose in the backward pass)
 is executed:
   * "dmma" -- hand-written FP64 tensor-core kernel (`csrc/dgemm_tri.cu`, DMMA.8x8x4);
-  * "int8" -- Ozaki-style error-free split onto the INT8 tensor cores (`csrc/ozaki_imma.cu`, tcgen05 + TMEM + TMA),
-              6 diagonals of signed 8-bit slices forward / 5 backward: same 1e-9 value and 1e-7 gradient parity, ~2x faster.
+  * "int8" -- Ozaki-style error-free split onto the INT8 tensor cores (`csrc/ozaki_imma.cu`, tcgen05 + TMEM + TMA).
+              The number of signed 8-bit slices (6 or 7 forward, 5..7 backward) is chosen PER FITTED MODEL by a build-time
+              probe around the training points so that the posterior variance stays within 1e-9 and gradients within
+              1e-7 of the FP64 contraction; a model that no slice count serves runs on "dmma"
+              (`DevicePredictionStrategy._select_int8`).  ~2x faster than "dmma".  This is the default.
+`int8_slices` = (g_fwd, g_bwd) pins the slice counts and skips the probe (benchmarks / developer tools only).
 """
 from __future__ import annotations
 
@@ -35,4 +39,5 @@ class _Flag:
         self._value = value
 
 
-contraction = _Flag("dmma")
+contraction = _Flag("int8")
+int8_slices = _Flag(None)

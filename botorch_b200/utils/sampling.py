@@ -109,3 +109,53 @@ def boltzmann_sample(function_values: Tensor, num_samples: int, eta: float, repl
         eta *= temp_decrease
         weights = torch.exp(eta * norm_weights)
     return batched_multinomial(weights=weights, num_samples=num_samples, replacement=replacement)
+
+
+def sample_truncated_normal_perturbations(X: Tensor, n_discrete_points: int, sigma: float, bounds: Tensor,
+                                          qmc: bool = True) -> Tensor:
+    """`n_discrete_points` points N(x, sigma^2 I) around randomly chosen rows x of `X`, truncated to the box by inverse-CDF
+    sampling in the normalised cube (reference utils/sampling.py:1118-1166)."""
+    Xn = (X - bounds[0]) / (bounds[1] - bounds[0])
+    d = Xn.shape[1]
+    if Xn.shape[0] > 1:
+        Xn = Xn[torch.randint(Xn.shape[0], (n_discrete_points,), device=Xn.device)]
+    if qmc:
+        std_bounds = torch.zeros(2, d, dtype=Xn.dtype, device=Xn.device)
+        std_bounds[1] = 1
+        u = draw_sobol_samples(bounds=std_bounds, n=n_discrete_points, q=1).squeeze(1)
+    else:
+        u = torch.rand((n_discrete_points, d), dtype=Xn.dtype, device=Xn.device)
+    normal = torch.distributions.Normal(0, 1)
+    cdf_alpha = normal.cdf(-Xn / sigma)
+    perturbation = normal.icdf(cdf_alpha + u * (normal.cdf((1 - Xn) / sigma) - cdf_alpha)) * sigma
+    return (Xn + perturbation).clamp(0.0, 1.0) * (bounds[1] - bounds[0]) + bounds[0]
+
+
+def sample_perturbed_subset_dims(X: Tensor, bounds: Tensor, n_discrete_points: int, sigma: float = 1e-1, qmc: bool = True,
+                                 prob_perturb: float | None = None) -> Tensor:
+    """Perturb a random subset of the dimensions (probability min(20/d, 1) each, at least `ceil(d p)` when none was hit)
+    of randomly chosen rows of `X` (reference utils/sampling.py:1169-1242)."""
+    from ..exceptions.errors import BotorchTensorDimensionError
+
+    if bounds.ndim != 2:
+        raise BotorchTensorDimensionError("bounds must be a `2 x d`-dim tensor.")
+    if X.ndim != 2:
+        raise BotorchTensorDimensionError("X must be a `n x d`-dim tensor.")
+    d = bounds.shape[-1]
+    if prob_perturb is None:
+        prob_perturb = min(20.0 / d, 1.0)
+    if X.shape[0] == 1:
+        X_cand = X.repeat(n_discrete_points, 1)
+    else:
+        X_cand = X[torch.randint(X.shape[0], (n_discrete_points,), device=X.device)]
+    pert = sample_truncated_normal_perturbations(X=X_cand, n_discrete_points=n_discrete_points, sigma=sigma, bounds=bounds,
+                                                 qmc=qmc)
+    mask = torch.rand(n_discrete_points, d, dtype=bounds.dtype, device=bounds.device) <= prob_perturb
+    ind = (~mask).all(dim=-1).nonzero()
+    n_perturb = math.ceil(d * prob_perturb)
+    perturb_mask = torch.zeros(d, dtype=mask.dtype, device=mask.device)
+    perturb_mask[:n_perturb].fill_(1)
+    for idx in ind:
+        mask[idx] = perturb_mask[torch.randperm(d, device=bounds.device)]
+    X_cand[mask] = pert[mask]
+    return X_cand

@@ -51,6 +51,7 @@ extern "C" {
 #define MCACQ_MAX_Q 32
 #define MCACQ_MAX_D 64
 #define MCACQ_MAX_R 64
+#define MCACQ_MAX_SLICES 7 /* int8 contraction: at most 7 signed 8-bit slices (54-bit fixed-point operands) */
 
 /* info[b] bits written by mcacq_acq_forward (psd_safe_cholesky semantics, max_tries = 6):   */
 #define MCACQ_INFO_JITTER_MASK 0x7 /* number of jitter escalations applied (0 = none, 1 -> 1e-8, ... 6 -> 1e-3) */
@@ -75,14 +76,15 @@ typedef struct {
   const double* R;           /* [np x np] covar_cache = L^{-T}, upper triangular, zero padded */
   const double* Rt;          /* [np x np] transpose of R (lower triangular), zero padded    */
   /* Optional INT8-tensor-core contraction (csrc/ozaki_imma.cu).  contraction = 0: FP64 DMMA (mcacq_dgemm_tri);
-   * contraction = 1: Ozaki split, g_fwd / g_bwd diagonals (6 / 5 keep 1e-9 on values / 1e-7 on gradients).      */
+   * contraction = 1: Ozaki split, g_fwd / g_bwd diagonals (<= MCACQ_MAX_SLICES; error ~2^-(8g-2) of row max x column max:
+   * the host picks the smallest g whose build-time probe meets 1e-9 on the variance / 1e-7 on gradients).          */
   int32_t contraction;
   int32_t g_fwd;
   int32_t g_bwd;
   int32_t _pad;
-  const int8_t* Rt_slices;   /* [6][np][np] row-scaled slices of R^T (row j = column j of R)  -- forward B operand */
+  const int8_t* Rt_slices;   /* [g_fwd][np][np] row-scaled slices of R^T (row j = column j of R)  -- forward B operand */
   const double* Rt_scale;    /* [np]                                                                             */
-  const int8_t* R_slices;    /* [6][np][np] row-scaled slices of R                            -- backward B operand */
+  const int8_t* R_slices;    /* [g_bwd][np][np] row-scaled slices of R                            -- backward B operand */
   const double* R_scale;     /* [np]                                                                             */
 } mcacq_model;
 
@@ -161,7 +163,10 @@ int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, 
 int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G, const int8_t* A_slices, const double* row_scale,
                          const int8_t* B_slices, const double* col_scale, double* C, int64_t ldc, void* stream);
 
+/* Workspace size of one forward(+backward) call.  `mcacq_workspace_bytes` is the bound over all contraction modes;
+ * `mcacq_workspace_bytes_model` is exact for the model's mode (the FP64 DMMA mode carries no int8 slice buffers).   */
 size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
+size_t mcacq_workspace_bytes_model(const mcacq_model* model, int64_t b, int q, int r);
 
 /* Posterior over b q-batches: mean [b x q], covar [b x q x q] on the original outcome scale. */
 int mcacq_posterior(const mcacq_model* model, const double* X, int64_t b, int q, double* mean, double* covar,

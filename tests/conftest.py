@@ -19,3 +19,34 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("CUDA not available")
     return torch.device("cuda:0")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device AND the built extension: skip them (instead of erroring at import or at the
+    first CUDA call) when either is missing, so a bare `pytest tests` is green on a CUDA-less box."""
+    import torch
+
+    from botorch_b200 import _lib
+
+    reason = None
+    if not torch.cuda.is_available():
+        reason = "CUDA not available"
+    elif not _lib._SO.exists():
+        reason = f"{_lib._SO.name} is not built"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _restore_settings():
+    """Tests flip the package-level flags; every test starts from and returns to the product defaults."""
+    from botorch_b200 import settings
+
+    saved = (settings.contraction.value(), settings.int8_slices.value())
+    yield
+    settings.contraction.set(saved[0])
+    settings.int8_slices.set(saved[1])
