@@ -40,8 +40,6 @@ def gen_candidates_scipy(initial_conditions: Tensor, acquisition_function, lower
                          use_parallel_mode: bool | None = None) -> tuple[Tensor, Tensor]:
     if inequality_constraints or equality_constraints or nonlinear_inequality_constraints or fixed_features:
         raise UnsupportedError("botorch_b200.gen_candidates_scipy implements the box-bounded L-BFGS-B fast path only.")
-    if timeout_sec is not None:
-        raise UnsupportedError("timeout_sec is not supported by the batched fast path.")
     options = dict(options or {})
     options.setdefault("maxiter", 2000)
     if options.get("method", "L-BFGS-B") != "L-BFGS-B" or not options.get("with_grad", True):
@@ -67,15 +65,40 @@ def gen_candidates_scipy(initial_conditions: Tensor, acquisition_function, lower
     xs, fs, results = fmin_l_bfgs_b_batched(
         func=partial(_f_np_wrapper, f=f, shapeX=clamped.shape, device=initial_conditions.device,
                      dtype=initial_conditions.dtype),
-        x0=x0, bounds=bounds, callback=options.get("callback"), pass_batch_indices=True, **minimize_opts)
+        x0=x0, bounds=bounds, callback=options.get("callback"), pass_batch_indices=True, timeout_sec=timeout_sec,
+        **minimize_opts)
     for res in results:
-        if not res.success:
-            msg = res.message if isinstance(res.message, str) else res.message.decode("ascii")
-            warnings.warn(f"Optimization failed within `scipy.optimize.minimize` with status {res.status} and "
-                          f"message {msg}.", OptimizationWarning, stacklevel=2)
+        _process_scipy_result(res=res, options=options)
     candidates = torch.from_numpy(xs).view_as(clamped).to(initial_conditions)
     clamped_candidates = columnwise_clamp(X=candidates, lower=lower_bounds, upper=upper_bounds,
                                           raise_on_violation=True).reshape(orig_shape)
     with torch.no_grad():
         batch_acquisition = acquisition_function(clamped_candidates)
     return clamped_candidates, batch_acquisition
+
+
+def _process_scipy_result(res, options: dict) -> None:
+    """Logs and warnings for one scipy result (reference generation/gen.py:711-746): running into the iteration /
+    evaluation limit or the timeout is logged, every other failure raises an `OptimizationWarning`."""
+    import logging
+
+    logger = logging.getLogger("botorch")
+    if "success" not in res.keys() or "status" not in res.keys():
+        with warnings.catch_warnings():
+            warnings.simplefilter("always", category=OptimizationWarning)
+            warnings.warn("Optimization failed within `scipy.optimize.minimize` with no status returned to `res.`",
+                          OptimizationWarning, stacklevel=3)
+    elif not res.success:
+        msg = res.message if isinstance(res.message, str) else res.message.decode("ascii")
+        if "ITERATIONS REACHED LIMIT" in msg or "Iteration limit reached" in msg:
+            logger.info(f"`scipy.optimize.minimize` exited by reaching the iteration limit of `maxiter: {options.get('maxiter')}`.")
+        elif "EVALUATIONS EXCEEDS LIMIT" in msg:
+            logger.info("`scipy.optimize.minimize` exited by reaching the function evaluation limit of "
+                        f"`maxfun: {options.get('maxfun')}`.")
+        elif "Optimization timed out after" in msg:
+            logger.info(msg)
+        else:
+            with warnings.catch_warnings():
+                warnings.simplefilter("always", category=OptimizationWarning)
+                warnings.warn(f"Optimization failed within `scipy.optimize.minimize` with status {res.status} and "
+                              f"message {msg}.", OptimizationWarning, stacklevel=3)

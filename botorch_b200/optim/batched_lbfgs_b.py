@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import os
 import threading
+import time
 from typing import Any, Callable
 
 import numpy as np
@@ -116,6 +117,14 @@ def _run_threads(func: Callable, x0: np.ndarray, bounds, maxiter: int, maxcor: i
 
 # ---- direct driver over scipy's reverse-communication routine ---------------------------------------------------------
 _STATUS = {0: "START", 1: "NEW_X", 2: "RESTART", 3: "FG", 4: "CONVERGENCE", 5: "STOP", 6: "WARNING", 7: "ERROR", 8: "ABNORMAL"}
+# scipy's `task_messages` (second task word): the message of an OptimizeResult is "<status>: <task message>"
+_TASK = {0: "", 301: "", 302: "", 401: "NORM OF PROJECTED GRADIENT <= PGTOL", 402: "RELATIVE REDUCTION OF F <= FACTR*EPSMCH",
+         501: "CPU EXCEEDING THE TIME LIMIT", 502: "TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT",
+         503: "PROJECTED GRADIENT IS SUFFICIENTLY SMALL", 504: "TOTAL NO. OF ITERATIONS REACHED LIMIT",
+         505: "CALLBACK REQUESTED HALT", 601: "ROUNDING ERRORS PREVENT PROGRESS", 602: "STP = STPMAX", 603: "STP = STPMIN",
+         604: "XTOL TEST SATISFIED", 701: "NO FEASIBLE SOLUTION", 702: "FACTR < 0", 703: "FTOL < 0", 704: "GTOL < 0",
+         705: "XTOL < 0", 706: "STP < STPMIN", 707: "STP > STPMAX", 708: "STPMIN < 0", 709: "STPMAX < STPMIN",
+         710: "INITIAL G >= 0", 711: "M <= 0", 712: "N <= 0", 713: "INVALID NBD"}
 
 
 class _Problem:
@@ -151,8 +160,11 @@ class _Problem:
 
 
 def _run_direct(setulb, int_dtype, func: Callable, x0: np.ndarray, bounds, maxiter: int, maxcor: int, ftol: float,
-                pgtol: float, maxls: int, maxfun: int, callback: Callable | None, pass_batch_indices: bool):
+                pgtol: float, maxls: int, maxfun: int, callback: Callable | None, pass_batch_indices: bool,
+                timeout_sec: float | None = None):
     N, D = x0.shape
+    start = time.monotonic()
+    timed_out: set[int] = set()
     factr = ftol / np.finfo(float).eps
     if not maxls > 0:
         raise ValueError("maxls must be positive.")
@@ -184,6 +196,12 @@ def _run_direct(setulb, int_dtype, func: Callable, x0: np.ndarray, bounds, maxit
                     break
                 if t == 1:  # a new iterate: callback and budget checks exactly where scipy's driver makes them
                     p.nit += 1
+                    if timeout_sec is not None and time.monotonic() - start > timeout_sec:
+                        # reference optim/utils/timeout.py:46-53: the per-iteration callback raises once the budget is
+                        # spent; the iterate of that moment is returned with status 1 (like maxiter)
+                        timed_out.add(i)
+                        p.task[0], p.task[1] = 5, 505
+                        continue
                     if callback is not None:
                         try:
                             callback(np.copy(p.x))
@@ -208,11 +226,14 @@ def _run_direct(setulb, int_dtype, func: Callable, x0: np.ndarray, bounds, maxit
                 p.nfev += 1
         active = need
     results = []
-    for p in probs:
+    runtime = time.monotonic() - start
+    for i, p in enumerate(probs):
         t = int(p.task[0])
-        warnflag = 0 if t == 4 else (1 if (p.nfev > maxfun or p.nit >= maxiter) else 2)
+        warnflag = 0 if t == 4 else (1 if (p.nfev > maxfun or p.nit >= maxiter or i in timed_out) else 2)
+        msg = (f"Optimization timed out after {runtime} seconds." if i in timed_out
+               else _STATUS.get(t, str(t)) + ": " + _TASK.get(int(p.task[1]), str(int(p.task[1]))))
         results.append(OptimizeResult(fun=float(p.f), jac=p.g, nfev=p.nfev, njev=p.nfev, nit=p.nit, status=warnflag,
-                                      message=_STATUS.get(t, str(t)), x=p.x, success=(warnflag == 0)))
+                                      message=msg, x=p.x, success=(warnflag == 0)))
     xs = np.stack([r.x for r in results])
     fs = np.array([r.fun for r in results])
     return xs, fs, results
@@ -264,6 +285,7 @@ def _direct_driver():
 def fmin_l_bfgs_b_batched(func: Callable, x0: np.ndarray, bounds=None, maxiter: int = 15000, maxcor: int = 10,
                           ftol: float = 2.2204460492503131e-09, pgtol: float = 1e-5, maxls: int = 20,
                           maxfun: int = 15000, callback: Callable | None = None, pass_batch_indices: bool = False,
+                          timeout_sec: float | None = None,
                           **unused: Any) -> tuple[np.ndarray, np.ndarray, list[OptimizeResult]]:
     """Minimise N problems `x0[i]` (N x D) sharing `func(X: K x D[, batch_indices]) -> (f: K, g: K x D)`.
 
@@ -276,5 +298,14 @@ def fmin_l_bfgs_b_batched(func: Callable, x0: np.ndarray, bounds=None, maxiter: 
     drv = _direct_driver()
     if drv is not None:
         return _run_direct(drv[0], drv[1], func, x0, bounds, maxiter, maxcor, ftol, pgtol, maxls, maxfun, callback,
-                           pass_batch_indices)
+                           pass_batch_indices, timeout_sec)
+    if timeout_sec is not None:
+        start, user_cb = time.monotonic(), callback
+
+        def callback(xk):  # noqa: F811 -- scipy's `minimize` stops a run whose callback raises StopIteration
+            if time.monotonic() - start > timeout_sec:
+                raise StopIteration
+            if user_cb is not None:
+                user_cb(xk)
+
     return _run_threads(func, x0, bounds, maxiter, maxcor, ftol, pgtol, maxls, maxfun, callback, pass_batch_indices)

@@ -15,7 +15,7 @@ installable in the build container, and no reference test pins numbers there.  T
 parts are restated from the published gpytorch 1.15 / linear_operator 0.6 algorithms
 (see `oracle/gp.py` docstrings).  The parts that ARE in the reference tree
 (`botorch/utils/safe_math.py`, `botorch/sampling/qmc.py`, `botorch/utils/sampling.py`)
-are pinned: `tests/test_oracle_vs_reference.py` checks the restatements against the
+are pinned: `tests/test_oracle_golden.py` checks the restatements against the
 reference modules imported from `/root/reference` (when present), and
 `tests/golden/` holds vectors generated from those reference modules
 (`tests/golden/make_golden.py`).
