@@ -74,6 +74,11 @@ __device__ __forceinline__ void oz_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(oz_smem_u32(bar)), "h"(mask) : "memory");
 }
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void oz_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -142,7 +147,8 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __shared__ __align__(8) uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ double s_col[OZ_MAX_BN];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction (and visibly so to ptxas)
   const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
   const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
   const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
@@ -175,82 +181,102 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
+  // Both single-thread roles run their loops in WARP-UNIFORM control flow and put only the asynchronous instructions under
+  // one elected lane.  With the loops inside an `if (lane == 0)` branch ptxas cannot keep the descriptors in uniform
+  // registers and wraps every UTCIMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~150 clk of dependent
+  // single-thread latency per instruction, plus a 64-bit division call per k-block for `it % stages`): the kernel was
+  // bound by the issue rate of its MMA thread, at 41 % tensor-pipe activity, not by the pipe (0.50 clk per accumulator
+  // column in tools/ubench_umma.cu) nor by TMA (profiles/r02_ozaki_issue_bound.md).
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      int64_t it = 0;  // k-block counter across tiles
-      OzTile tl;
-      uint64_t pol_keep;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters) {
-        const int row0 = (int)((tl.mt * CM + rm) * OZ_BM), col0 = (tl.nt * CN + rn) * OZ_BN;
-        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
-          const int s = (int)(it % stages);
-          if (it >= stages) oz_mbar_wait(&empty_bar[s], (uint32_t)(((it / stages) - 1) & 1));
-          if (dbg & 2) { oz_mbar_arrive(&full_bar[s]); continue; }
-          oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          uint8_t* st = smem + (size_t)s * stage_bytes;
-          if (CSIZE == 1 && (dbg & 4)) {
-            // the maps were encoded with a box depth of G slices: the slice-major stage layout is the same
-            oz_tma_3d(st, &mapA, &full_bar[s], kb * OZ_BK, row0, 0);
-            oz_tma_3d_hint(st + G * OZ_A_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, 0, pol_keep);
-          } else if (CSIZE == 1 && l2_hints) {
-            // the B slices (the triangular factor, re-used by every row tile of the launch) are kept in L2 with
-            // evict_last; the A slices are only re-used by the column tiles of the current row group
-            for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
-            for (int q = 0; q < G; q++)
-              oz_tma_3d_hint(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, pol_keep);
-          } else if (CSIZE == 1) {
-            for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
-            for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
+    // ================= TMA producer =================
+    const bool lead = oz_elect_one();
+    int s = 0;            // ring slot
+    uint32_t round = 0;   // number of times the ring has wrapped
+    OzTile tl;
+    uint64_t pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters) {
+      const int row0 = (int)((tl.mt * CM + rm) * OZ_BM), col0 = (tl.nt * CN + rn) * OZ_BN;
+      for (int kb = tl.kb0; kb < tl.kb1; kb++) {
+        if (round > 0) oz_mbar_wait(&empty_bar[s], (round - 1) & 1u);
+        if (lead) {
+          if (dbg & 2) {
+            oz_mbar_arrive(&full_bar[s]);
           } else {
-            // each CTA fetches 1/CN of its row's A slices and 1/CM of its column's B slices and multicasts them
-            for (int p = rn; p < G; p += CN) oz_tma_3d_mc(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p, row_mask);
-            for (int q = rm; q < G; q += CM) oz_tma_3d_mc(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, col_mask);
+            oz_mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            if (CSIZE == 1 && (dbg & 4)) {
+              // the maps were encoded with a box depth of G slices: the slice-major stage layout is the same
+              oz_tma_3d(st, &mapA, &full_bar[s], kb * OZ_BK, row0, 0);
+              oz_tma_3d_hint(st + G * OZ_A_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, 0, pol_keep);
+            } else if (CSIZE == 1 && l2_hints) {
+              // the B slices (the triangular factor, re-used by every row tile of the launch) are kept in L2 with
+              // evict_last; the A slices are only re-used by the column tiles of the current row group
+              for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
+              for (int q = 0; q < G; q++)
+                oz_tma_3d_hint(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, pol_keep);
+            } else if (CSIZE == 1) {
+              for (int p = 0; p < G; p++) oz_tma_3d(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p);
+              for (int q = 0; q < G; q++) oz_tma_3d(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q);
+            } else {
+              // each CTA fetches 1/CN of its row's A slices and 1/CM of its column's B slices and multicasts them
+              for (int p = rn; p < G; p += CN) oz_tma_3d_mc(st + p * OZ_A_TILE, &mapA, &full_bar[s], kb * OZ_BK, row0, p, row_mask);
+              for (int q = rm; q < G; q += CM) oz_tma_3d_mc(st + G * OZ_A_TILE + q * OZ_B_TILE, &mapB, &full_bar[s], kb * OZ_BK, col0, q, col_mask);
+            }
           }
         }
+        __syncwarp();
+        if (++s == stages) { s = 0; round++; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      // instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128; N is filled in per instruction
-      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
-      int64_t it = 0, tile_i = 0;
-      OzTile tl;
-      for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
-        if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
-          oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        for (int kb = tl.kb0; kb < tl.kb1; kb++, it++) {
-          const int s = (int)(it % stages);
-          oz_mbar_wait(&full_bar[s], (uint32_t)((it / stages) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint8_t* st = smem + (size_t)s * stage_bytes;
+    // ================= MMA issuer =================
+    const bool lead = oz_elect_one();
+    // instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128; N is filled in per instruction
+    const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+    const uint64_t desc0 = oz_desc<OZ_BK>(smem);   // descriptor of ring slot 0; tiles advance its 16-byte address field
+    int s = 0;
+    uint32_t round = 0;
+    int64_t tile_i = 0;
+    OzTile tl;
+    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
+      if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
+        oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int kb = tl.kb0; kb < tl.kb1; kb++) {
+        oz_mbar_wait(&full_bar[s], round & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lead) {
+          const uint64_t ds = desc0 + (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
           const bool first = (kb == tl.kb0);
           // A_p times the stacked tiles [B_0; ...; B_{G-1-p}] lands in the consecutive accumulators g = p .. G-1, so the
           // G(G+1)/2 slice products of a K=32 step are issued as wide UMMAs (N up to 256) instead of G(G+1)/2 N=64 ones:
           // the A tile is read from shared memory once per p, not once per pair.
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int k = 0; k < OZ_BK / 32; k++) {
-            if (dbg & 1) break;
-            for (int p = 0; p < G; p++) {
-              const uint64_t ad = oz_desc<OZ_BK>(st + p * OZ_A_TILE) + 2 * k;
-              const int ncols = (G - p) * OZ_BN;
-              for (int c0 = 0; c0 < ncols; c0 += 256) {
-                const int nn = (ncols - c0 < 256) ? (ncols - c0) : 256;
-                const uint64_t bd = oz_desc<OZ_BK>(st + G * OZ_A_TILE + c0 * OZ_BK) + 2 * k;  // stacked slices are contiguous rows
-                const uint32_t idesc_n = idesc_base | ((uint32_t)(nn >> 3) << 17);
-                oz_umma(tmem_base + (uint32_t)(p * OZ_BN + c0), ad, bd, idesc_n, (first && p == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < OZ_BK / 32; k++) {
+              for (int p = 0; p < G; p++) {
+                const uint64_t ad = ds + (uint64_t)((uint32_t)(p * OZ_A_TILE) >> 4) + 2 * k;
+                const int ncols = (G - p) * OZ_BN;
+                for (int c0 = 0; c0 < ncols; c0 += 256) {
+                  const int nn = (ncols - c0 < 256) ? (ncols - c0) : 256;
+                  // stacked slices are contiguous rows behind the G A tiles
+                  const uint64_t bd = ds + (uint64_t)((uint32_t)(G * OZ_A_TILE + c0 * OZ_BK) >> 4) + 2 * k;
+                  const uint32_t idesc_n = idesc_base | ((uint32_t)(nn >> 3) << 17);
+                  oz_umma(tmem_base + (uint32_t)(p * OZ_BN + c0), ad, bd, idesc_n, (first && p == 0 && k == 0) ? 0u : 1u);
+                }
               }
             }
           }
           if (CSIZE == 1) oz_commit(&empty_bar[s]);
           else oz_commit_mc(&empty_bar[s], release_mask);
         }
-        oz_commit(&acc_full);
+        __syncwarp();
+        if (++s == stages) { s = 0; round++; }
       }
+      if (lead) oz_commit(&acc_full);
+      __syncwarp();
     }
   } else {
     // ================= epilogue (warps 2..5) =================

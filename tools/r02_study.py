@@ -96,7 +96,7 @@ def contract():
     lines = []
 
     def run(G, env, tri=0):
-        for k in ("MCACQ_OZ_DEBUG", "MCACQ_OZ_STAGES", "MCACQ_OZ_BN", "MCACQ_OZ_BK", "MCACQ_OZ_GROUP", "MCACQ_OZ_HINT"):
+        for k in ("MCACQ_OZ_DEBUG", "MCACQ_OZ_STAGES", "MCACQ_OZ_BN", "MCACQ_OZ_BK", "MCACQ_OZ_GROUP", "MCACQ_OZ_HINT", "MCACQ_OZ_TMASTORE"):
             os.environ.pop(k, None)
         os.environ.update({k: str(v) for k, v in env.items()})
         As = torch.empty(G, M, n, dtype=torch.int8, device=dev)
@@ -125,27 +125,35 @@ def contract():
         print(lines[-1], flush=True)
         del As, Bs, C
 
-    for G in (5, 6, 7):
-        run(G, {})
-        run(G, {"MCACQ_OZ_DEBUG": 1})   # no UMMA: TMA ingest alone
-        run(G, {"MCACQ_OZ_DEBUG": 2})   # no TMA: UMMA + epilogue alone
-        run(G, {"MCACQ_OZ_DEBUG": 3})   # neither: barrier/epilogue skeleton
-        run(G, {"MCACQ_OZ_DEBUG": 4})   # one TMA box per operand over all G slices
-        run(G, {"MCACQ_OZ_DEBUG": 5})
-        run(G, {"MCACQ_OZ_STAGES": 1})
-        run(G, {"MCACQ_OZ_BN": 64})
-        run(G, {"MCACQ_OZ_BN": 64, "MCACQ_OZ_DEBUG": 1})
-        run(G, {"MCACQ_OZ_BN": 64, "MCACQ_OZ_DEBUG": 2})
-        run(G, {"MCACQ_OZ_HINT": 0})
-    run(6, {}, tri=1)
-    run(5, {}, tri=1)
-    run(3, {})
-    run(3, {"MCACQ_OZ_DEBUG": 1})
-    run(3, {"MCACQ_OZ_DEBUG": 2})
-    run(3, {"MCACQ_OZ_BK": 64})
-    run(3, {"MCACQ_OZ_BK": 64, "MCACQ_OZ_DEBUG": 1})
-    run(3, {"MCACQ_OZ_BK": 64, "MCACQ_OZ_DEBUG": 2})
-    open(f"{OUT}/r02_study_contract.txt", "w").write("\n".join(lines) + "\n")
+    which = sys.argv[2] if len(sys.argv) > 2 else "full"
+    if which == "epilogue":
+        for G in (5, 6, 7):
+            run(G, {})
+            run(G, {"MCACQ_OZ_TMASTORE": 0})
+            run(G, {"MCACQ_OZ_DEBUG": 2})
+            run(G, {"MCACQ_OZ_DEBUG": 3})
+        run(6, {}, tri=1)
+        run(5, {}, tri=1)
+        # the tensor core's shared-memory operand rate: pure N = 256 instructions (G = 1, BN = 256), MMA only
+        for G in (1, 2):
+            run(G, {"MCACQ_OZ_BK": 64})
+            run(G, {"MCACQ_OZ_BK": 64, "MCACQ_OZ_DEBUG": 2})
+            run(G, {"MCACQ_OZ_BK": 64, "MCACQ_OZ_DEBUG": 3})
+            run(G, {"MCACQ_OZ_BK": 128})
+            run(G, {"MCACQ_OZ_BK": 128, "MCACQ_OZ_DEBUG": 2})
+    else:
+        for G in (5, 6, 7):
+            run(G, {})
+            run(G, {"MCACQ_OZ_DEBUG": 1})   # no UMMA: TMA ingest alone
+            run(G, {"MCACQ_OZ_DEBUG": 2})   # no TMA: UMMA + epilogue alone
+            run(G, {"MCACQ_OZ_DEBUG": 3})   # neither: barrier/epilogue skeleton
+            run(G, {"MCACQ_OZ_DEBUG": 4})   # one TMA box per operand over all G slices
+            run(G, {"MCACQ_OZ_STAGES": 1})
+            run(G, {"MCACQ_OZ_BN": 64})
+            run(G, {"MCACQ_OZ_HINT": 0})
+        run(6, {}, tri=1)
+        run(5, {}, tri=1)
+    open(f"{OUT}/r02_study_contract_{which}.txt", "w").write("\n".join(lines) + "\n")
 
 
 if __name__ == "__main__":
