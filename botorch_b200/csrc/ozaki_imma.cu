@@ -131,6 +131,126 @@ __device__ __forceinline__ bool oz_tile(int64_t t, int64_t m_tiles, int n_tiles,
   return true;
 }
 
+// Epilogue role (warps 2..5) shared by the contraction kernels: thread <-> TMEM lane <-> output row.
+template <int OZ_BK, int OZ_BN, int CM, int CN>
+__device__ __forceinline__ void oz_epilogue(const CUtensorMap& mapC, int tri_mode, int64_t M, int N, int G,
+                                            const double* __restrict__ row_scale, const double* __restrict__ col_scale,
+                                            double* __restrict__ C, int64_t ldc, int l2_hints, int group_m, int tma_store,
+                                            int64_t m_tiles, int n_tiles, int k_blocks, int64_t cluster_id, int64_t num_clusters,
+                                            int rm, int rn, int warp, int lane, int tid, uint32_t tmem_base, uint64_t& acc_full,
+                                            uint64_t& acc_empty_ref, double* s_col, uint8_t* epi_stage) {
+  uint64_t* acc_full_p = &acc_full;
+  uint64_t* acc_empty_p = &acc_empty_ref;
+  const int lg = warp & 3;                  // TMEM lane group this warp may access
+  const int r_in_tile = lg * 32 + lane;
+  const int etid = tid - 64;                // 0..127
+  int64_t tile_i = 0;
+  OzTile tl;
+  // output staging: 2 x 4 KB (32 rows x 128 B, SWIZZLE_128B) per epilogue warp, behind the operand ring
+  epi_stage = (uint8_t*)(((uintptr_t)epi_stage + 1023) & ~(uintptr_t)1023);
+  uint32_t epi_chunk = 0;
+  for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
+    const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
+    const int col0 = (tl.nt * CN + rn) * OZ_BN;
+    // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
+    for (int c = etid; c < OZ_BN; c += 128) s_col[c] = (col0 + c < N) ? col_scale[col0 + c] : 0.0;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const bool have_acc = tl.kb1 > tl.kb0;
+    if (have_acc) {
+      oz_mbar_wait(acc_full_p, (uint32_t)(tile_i & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const bool row_ok = row < M;
+    const double rs = row_ok ? row_scale[row] : 0.0;
+    double* dst = C + (row_ok ? row : 0) * ldc + col0;
+    const bool vec_ok = (ldc & 1) == 0;
+    // 16 output columns at a time: all G diagonals of the chunk are fetched from TMEM, combined in fp64 with the
+    // weights 256^-(g+2) and scaled.  Output: the warp's 32 rows x 16 columns are staged in shared memory in the
+    // SWIZZLE_128B layout (conflict-free 16-byte stores) and written by ONE TMA store per chunk, i.e. as full 128-byte
+    // lines -- a thread-per-row store pattern hits 32 different lines per instruction with half-filled sectors and made
+    // the epilogue (which cannot overlap the main loop: all 512 TMEM columns hold accumulators) 23 % of the kernel.
+#pragma unroll 1
+    for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+      double acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) acc[j] = 0.0;
+      if (have_acc) {
+        uint32_t v[OZ_MAXG][16];
+#pragma unroll
+        for (int g = 0; g < OZ_MAXG; g++) {
+          if (g < G) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]), "=r"(v[g][6]),
+                           "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]), "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]),
+                           "=r"(v[g][13]), "=r"(v[g][14]), "=r"(v[g][15])
+                         : "r"(taddr));
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // Three neighbouring diagonals are merged exactly in int64 (|S_g| < 2^31, so the sum stays below 2^48) and
+        // converted with the 2^52 + 2^51 magic constant: one DADD + one DFMA per triple instead of an I2F.F64 (16/clk/SM)
+        // and a DFMA per diagonal.
+        double w = 1.0 / 4294967296.0;  // 256^-4: weight of the last member of the triple (S_0, S_1, S_2)
+#pragma unroll
+        for (int g0 = 0; g0 < OZ_MAXG; g0 += 3) {
+          if (g0 < G) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const long long s0 = (long long)(int32_t)v[g0][j];
+              const long long s1 = (g0 + 1 < OZ_MAXG && g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1 < OZ_MAXG ? g0 + 1 : g0][j] : 0ll;
+              const long long s2 = (g0 + 2 < OZ_MAXG && g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2 < OZ_MAXG ? g0 + 2 : g0][j] : 0ll;
+              const long long t = s0 * 65536ll + s1 * 256ll + s2;
+              const double d = __longlong_as_double(0x4338000000000000ll + t) - 6755399441055744.0;
+              acc[j] = fma(w, d, acc[j]);
+            }
+            w *= (1.0 / 16777216.0);
+          }
+        }
+      }
+      if (tma_store) {
+        if (col0 + c0 < N) {   // warp-uniform
+          uint8_t* sbuf = epi_stage + (size_t)((lg * 2 + (epi_chunk & 1)) * 4096);
+          // the store issued two chunks ago read from this buffer: it must have finished reading before we overwrite
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+            *reinterpret_cast<double2*>(sbuf + lane * 128 + ((((j >> 1) ^ (lane & 7))) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&mapC), "r"(oz_smem_u32(sbuf)), "r"(col0 + c0), "r"((int)((tl.mt * CM + rm) * OZ_BM + lg * 32)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          epi_chunk++;
+        }
+      } else if (row_ok && col0 + c0 < N) {
+        if (col0 + c0 + 16 <= N && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
+            if (l2_hints) __stcs(reinterpret_cast<double2*>(dst + c0 + j), o);  // streamed: consumed by a later kernel
+            else *reinterpret_cast<double2*>(dst + c0 + j) = o;
+          }
+        } else {
+          for (int j = 0; j < 16; j++) if (col0 + c0 + j < N) dst[c0 + j] = acc[j] * rs * s_col[c0 + j];
+        }
+      }
+    }
+    // hand the accumulators back (also for an empty k-range, which cannot happen for the triangular factors, so
+    // that the MMA thread's phase bookkeeping stays aligned)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) oz_mbar_arrive(acc_empty_p);
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // s_col reuse
+  }
+  if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+}
+
 template <int OZ_BK, int OZ_BN, int CM, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -280,119 +400,168 @@ ozaki_imma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else {
     // ================= epilogue (warps 2..5) =================
-    const int lg = warp & 3;                  // TMEM lane group this warp may access
-    const int r_in_tile = lg * 32 + lane;
-    const int etid = tid - 64;                // 0..127
-    int64_t tile_i = 0;
-    OzTile tl;
-    // output staging: 2 x 4 KB (32 rows x 128 B, SWIZZLE_128B) per epilogue warp, behind the operand ring
-    uint8_t* epi_stage = smem + (size_t)stages * stage_bytes;
-    epi_stage = (uint8_t*)(((uintptr_t)epi_stage + 1023) & ~(uintptr_t)1023);
-    uint32_t epi_chunk = 0;
-    for (int64_t t = cluster_id; oz_tile<OZ_BK, OZ_BN, CM, CN>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_clusters, tile_i++) {
-      const int64_t row = (tl.mt * CM + rm) * OZ_BM + r_in_tile;
-      const int col0 = (tl.nt * CN + rn) * OZ_BN;
-      // stage the column scales of this tile (epilogue-only named barrier, 128 threads)
-      for (int c = etid; c < OZ_BN; c += 128) s_col[c] = (col0 + c < N) ? col_scale[col0 + c] : 0.0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const bool have_acc = tl.kb1 > tl.kb0;
-      if (have_acc) {
-        oz_mbar_wait(&acc_full, (uint32_t)(tile_i & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      const bool row_ok = row < M;
-      const double rs = row_ok ? row_scale[row] : 0.0;
-      double* dst = C + (row_ok ? row : 0) * ldc + col0;
-      const bool vec_ok = (ldc & 1) == 0;
-      // 16 output columns at a time: all G diagonals of the chunk are fetched from TMEM, combined in fp64 with the
-      // weights 256^-(g+2) and scaled.  Output: the warp's 32 rows x 16 columns are staged in shared memory in the
-      // SWIZZLE_128B layout (conflict-free 16-byte stores) and written by ONE TMA store per chunk, i.e. as full 128-byte
-      // lines -- a thread-per-row store pattern hits 32 different lines per instruction with half-filled sectors and made
-      // the epilogue (which cannot overlap the main loop: all 512 TMEM columns hold accumulators) 23 % of the kernel.
-#pragma unroll 1
-      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-        double acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] = 0.0;
-        if (have_acc) {
-          uint32_t v[OZ_MAXG][16];
-#pragma unroll
-          for (int g = 0; g < OZ_MAXG; g++) {
-            if (g < G) {
-              const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * OZ_BN + c0);
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                           : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]), "=r"(v[g][6]),
-                             "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]), "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]),
-                             "=r"(v[g][13]), "=r"(v[g][14]), "=r"(v[g][15])
-                           : "r"(taddr));
-            }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          // Three neighbouring diagonals are merged exactly in int64 (|S_g| < 2^31, so the sum stays below 2^48) and
-          // converted with the 2^52 + 2^51 magic constant: one DADD + one DFMA per triple instead of an I2F.F64 (16/clk/SM)
-          // and a DFMA per diagonal.
-          double w = 1.0 / 4294967296.0;  // 256^-4: weight of the last member of the triple (S_0, S_1, S_2)
-#pragma unroll
-          for (int g0 = 0; g0 < OZ_MAXG; g0 += 3) {
-            if (g0 < G) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) {
-                const long long s0 = (long long)(int32_t)v[g0][j];
-                const long long s1 = (g0 + 1 < OZ_MAXG && g0 + 1 < G) ? (long long)(int32_t)v[g0 + 1 < OZ_MAXG ? g0 + 1 : g0][j] : 0ll;
-                const long long s2 = (g0 + 2 < OZ_MAXG && g0 + 2 < G) ? (long long)(int32_t)v[g0 + 2 < OZ_MAXG ? g0 + 2 : g0][j] : 0ll;
-                const long long t = s0 * 65536ll + s1 * 256ll + s2;
-                const double d = __longlong_as_double(0x4338000000000000ll + t) - 6755399441055744.0;
-                acc[j] = fma(w, d, acc[j]);
-              }
-              w *= (1.0 / 16777216.0);
-            }
-          }
-        }
-        if (tma_store) {
-          if (col0 + c0 < N) {   // warp-uniform
-            uint8_t* sbuf = epi_stage + (size_t)((lg * 2 + (epi_chunk & 1)) * 4096);
-            // the store issued two chunks ago read from this buffer: it must have finished reading before we overwrite
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
-              *reinterpret_cast<double2*>(sbuf + lane * 128 + ((((j >> 1) ^ (lane & 7))) << 4)) = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(&mapC), "r"(oz_smem_u32(sbuf)), "r"(col0 + c0), "r"((int)((tl.mt * CM + rm) * OZ_BM + lg * 32)) : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            epi_chunk++;
-          }
-        } else if (row_ok && col0 + c0 < N) {
-          if (col0 + c0 + 16 <= N && vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const double2 o = make_double2(acc[j] * rs * s_col[c0 + j], acc[j + 1] * rs * s_col[c0 + j + 1]);
-              if (l2_hints) __stcs(reinterpret_cast<double2*>(dst + c0 + j), o);  // streamed: consumed by a later kernel
-              else *reinterpret_cast<double2*>(dst + c0 + j) = o;
-            }
-          } else {
-            for (int j = 0; j < 16; j++) if (col0 + c0 + j < N) dst[c0 + j] = acc[j] * rs * s_col[c0 + j];
-          }
-        }
-      }
-      // hand the accumulators back (also for an empty k-range, which cannot happen for the triangular factors, so
-      // that the MMA thread's phase bookkeeping stays aligned)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) oz_mbar_arrive(&acc_empty);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // s_col reuse
-    }
-    if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+    oz_epilogue<OZ_BK, OZ_BN, CM, CN>(mapC, tri_mode, M, N, G, row_scale, col_scale, C, ldc, l2_hints, group_m, tma_store, m_tiles,
+                                      n_tiles, k_blocks, cluster_id, num_clusters, rm, rn, warp, lane, tid, tmem_base, acc_full,
+                                      acc_empty, s_col, smem + (size_t)stages * stage_bytes);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (CSIZE > 1) oz_cluster_sync();   // no CTA leaves while a peer may still signal its barriers
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ---- split-ring variant (experiment, MCACQ_OZ_RING=1; measured SLOWER) ---------------------------------------------
+// Same tile, same instructions, finer pipeline.  With whole k-blocks as ring stages only two 80 KB stages fit, so while the
+// tensor pipe works on one stage exactly ONE refill is in flight: 9.1 ms at G = 6 with MMA-only 7.5 ms and TMA-only 5.7 ms
+// (profiles/r02_ozaki_variants_uniform_issue.txt).  Here the B slices of a k-block (G x BN rows) are double-buffered as a
+// block and the A slices (128 rows each) go through a ring of NA 8 KB slots with one mbarrier pair per slot, so that 2-3
+// k-blocks of A tiles are in flight.  Result (profiles/r02_ozaki_ring.txt): 11.8 ms instead of 8.8 ms at G = 6 -- the G
+// extra wait / fence / commit round trips per k-block stall the instruction stream of BOTH single-lane roles (MMA-only
+// 11.0 ms, TMA-only 10.2 ms): barrier traffic costs more than the deeper pipeline gains.  Kept for the record.
+constexpr int OZ_MAX_NA = 20;
+
+template <int OZ_BN>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapC, int tri_mode, int64_t M, int N, int K, int G, int NA,
+                  const double* __restrict__ row_scale, const double* __restrict__ col_scale, double* __restrict__ C,
+                  int64_t ldc, int l2_hints, int group_m, int dbg, int tma_store) {
+  constexpr int OZ_BK = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int OZ_A_TILE = OZ_BM * OZ_BK, OZ_B_TILE = OZ_BN * OZ_BK;
+  const int b_block = G * OZ_B_TILE;            // one k-block of stacked B slices
+  uint8_t* sB = smem;                           // [2][G][BN x 64 B]
+  uint8_t* sA = smem + 2 * (size_t)b_block;     // [NA][128 x 64 B]
+  __shared__ __align__(8) uint64_t fullA[OZ_MAX_NA], emptyA[OZ_MAX_NA], fullB[2], emptyB[2], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double s_col[OZ_MAX_BN];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t m_tiles = (M + OZ_BM - 1) / OZ_BM;
+  const int n_tiles = (N + OZ_BN - 1) / OZ_BN;
+  const int k_blocks = (K + OZ_BK - 1) / OZ_BK;
+  const int64_t cta_id = blockIdx.x, num_ctas = gridDim.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < NA; i++) { oz_mbar_init(&fullA[i], 1); oz_mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < 2; i++) { oz_mbar_init(&fullB[i], 1); oz_mbar_init(&emptyB[i], 1); }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ================= TMA producer (warp-uniform loops, one elected lane issues) =================
+    const bool lead = oz_elect_one();
+    int aslot = 0, bbuf = 0;
+    uint32_t around = 0, bround = 0;   // wrap counts of the A ring / B double buffer
+    OzTile tl;
+    uint64_t pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    for (int64_t t = cta_id; oz_tile<OZ_BK, OZ_BN, 1, 1>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_ctas) {
+      const int row0 = (int)(tl.mt * OZ_BM), col0 = tl.nt * OZ_BN;
+      for (int kb = tl.kb0; kb < tl.kb1; kb++) {
+        // B block of this k-block
+        if (bround > 0) oz_mbar_wait(&emptyB[bbuf], (bround - 1) & 1u);
+        if (lead) {
+          if (dbg & 2) {
+            oz_mbar_arrive(&fullB[bbuf]);
+          } else {
+            oz_mbar_expect_tx(&fullB[bbuf], (uint32_t)b_block);
+            uint8_t* dst = sB + (size_t)bbuf * b_block;
+            // the B slices (the triangular factor, re-used by every row tile of the launch) stay in L2 with evict_last
+            for (int q = 0; q < G; q++) {
+              if (l2_hints) oz_tma_3d_hint(dst + q * OZ_B_TILE, &mapB, &fullB[bbuf], kb * OZ_BK, col0, q, pol_keep);
+              else oz_tma_3d(dst + q * OZ_B_TILE, &mapB, &fullB[bbuf], kb * OZ_BK, col0, q);
+            }
+          }
+        }
+        __syncwarp();
+        bbuf ^= 1;
+        if (bbuf == 0) bround++;
+        // A slices, one ring slot each
+        for (int p = 0; p < G; p++) {
+          if (around > 0) oz_mbar_wait(&emptyA[aslot], (around - 1) & 1u);
+          if (lead) {
+            if (dbg & 2) {
+              oz_mbar_arrive(&fullA[aslot]);
+            } else {
+              oz_mbar_expect_tx(&fullA[aslot], (uint32_t)OZ_A_TILE);
+              oz_tma_3d(sA + (size_t)aslot * OZ_A_TILE, &mapA, &fullA[aslot], kb * OZ_BK, row0, p);
+            }
+          }
+          __syncwarp();
+          if (++aslot == NA) { aslot = 0; around++; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const bool lead = oz_elect_one();
+    const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+    const uint64_t descB0 = oz_desc<OZ_BK>(sB), descA0 = oz_desc<OZ_BK>(sA);
+    int aslot = 0, bbuf = 0;
+    uint32_t around = 0, bround = 0;
+    int64_t tile_i = 0;
+    OzTile tl;
+    for (int64_t t = cta_id; oz_tile<OZ_BK, OZ_BN, 1, 1>(t, m_tiles, n_tiles, k_blocks, tri_mode, group_m, tl); t += num_ctas, tile_i++) {
+      if (tile_i > 0) {  // accumulators must have been drained by the epilogue of the previous tile
+        oz_mbar_wait(&acc_empty, (uint32_t)((tile_i - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int kb = tl.kb0; kb < tl.kb1; kb++) {
+        oz_mbar_wait(&fullB[bbuf], bround & 1u);
+        const uint64_t db = descB0 + (uint64_t)((uint32_t)(bbuf * b_block) >> 4);
+        const bool first = (kb == tl.kb0);
+        for (int p = 0; p < G; p++) {
+          oz_mbar_wait(&fullA[aslot], around & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lead) {
+            // A_p times the stacked tiles [B_0; ...; B_{G-1-p}] lands in the consecutive accumulators g = p .. G-1: wide
+            // UMMAs (N up to 256); the very first instruction of a tile (p = 0, k = 0) covers all G * BN columns and
+            // overwrites them, everything after accumulates
+            if (!(dbg & 1)) {
+              const uint64_t da = descA0 + (uint64_t)((uint32_t)(aslot * OZ_A_TILE) >> 4);
+              const int ncols = (G - p) * OZ_BN;
+#pragma unroll
+              for (int k = 0; k < OZ_BK / 32; k++) {
+                for (int c0 = 0; c0 < ncols; c0 += 256) {
+                  const int nn = (ncols - c0 < 256) ? (ncols - c0) : 256;
+                  const uint64_t bd = db + (uint64_t)((uint32_t)(c0 * OZ_BK) >> 4) + 2 * k;   // stacked slices are contiguous rows
+                  const uint32_t idesc_n = idesc_base | ((uint32_t)(nn >> 3) << 17);
+                  oz_umma(tmem_base + (uint32_t)(p * OZ_BN + c0), da + 2 * k, bd, idesc_n, (first && p == 0 && k == 0) ? 0u : 1u);
+                }
+              }
+            }
+            oz_commit(&emptyA[aslot]);
+          }
+          __syncwarp();
+          if (++aslot == NA) { aslot = 0; around++; }
+        }
+        if (lead) oz_commit(&emptyB[bbuf]);
+        __syncwarp();
+        bbuf ^= 1;
+        if (bbuf == 0) bround++;
+      }
+      if (lead) oz_commit(&acc_full);
+      __syncwarp();
+    }
+  } else {
+    oz_epilogue<OZ_BK, OZ_BN, 1, 1>(mapC, tri_mode, M, N, G, row_scale, col_scale, C, ldc, l2_hints, group_m, tma_store, m_tiles,
+                                    n_tiles, k_blocks, cta_id, num_ctas, 0, 0, warp, lane, tid, tmem_base, acc_full, acc_empty, s_col,
+                                    sA + (size_t)NA * OZ_A_TILE);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
@@ -775,6 +944,30 @@ static int oz_launch2_t(const CUtensorMap& mapA, const CUtensorMap& mapBh, int t
   return 0;
 }
 
+template <int OZ_BN>
+static int oz_launch_ring_t(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC, int tma_store, int tri_mode,
+                            int64_t M, int N, int K, int G, int NA, size_t smem, size_t smem_budget, const double* row_scale,
+                            const double* col_scale, double* C, int64_t ldc, cudaStream_t st, int dbg) {
+  auto kern = ozaki_ring_kernel<OZ_BN>;
+  static int sms = -1;
+  if (sms < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget + 1024));
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int l2_hints = (getenv("MCACQ_OZ_HINT") != nullptr) ? atoi(getenv("MCACQ_OZ_HINT")) : 1;
+  const int group_m = (getenv("MCACQ_OZ_GROUP") != nullptr) ? atoi(getenv("MCACQ_OZ_GROUP")) : OZ_GROUP_M;
+  const int64_t tiles = ((M + OZ_BM - 1) / OZ_BM) * ((N + OZ_BN - 1) / OZ_BN);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  kern<<<grid, OZ_THREADS, smem, st>>>(mapA, mapB, mapC, tri_mode, M, N, K, G, NA, row_scale, col_scale, C, ldc, l2_hints, group_m,
+                                       dbg, tma_store);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
 static int oz_launch(int bk, int bn, int cm, int cn, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
                      int tma_store, int tri_mode, int64_t M,
                      int N, int K, int G, int stages, size_t smem, size_t smem_budget, const double* row_scale,
@@ -853,7 +1046,16 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   }
   CUtensorMap mapA, mapB;
   int rc;
-  const int dbg = (getenv("MCACQ_OZ_DEBUG") != nullptr) ? atoi(getenv("MCACQ_OZ_DEBUG")) : 0;
+  int dbg = (getenv("MCACQ_OZ_DEBUG") != nullptr) ? atoi(getenv("MCACQ_OZ_DEBUG")) : 0;
+  // One TMA box per operand and k-block spanning all G slices (the slice-major stage layout is exactly a 3-D box): 2
+  // instead of 2 G bulk-tensor instructions per k-block, 8-13 % faster (G = 6: 9.15 -> 8.29 ms, G = 7: 12.1 -> 10.5 ms).
+  // Kernel flag bit 2; MCACQ_OZ_BOX=0 restores one box per slice.  Cluster (multicast) variants split the slices between
+  // the CTAs and keep per-slice boxes.
+  int cm_env = 1, cn_env = 1;
+  if (getenv("MCACQ_OZ_CLUSTER") != nullptr) { int v = atoi(getenv("MCACQ_OZ_CLUSTER")); cm_env = v / 10; cn_env = v % 10; }
+  const int one_box = (getenv("MCACQ_OZ_BOX") != nullptr) ? atoi(getenv("MCACQ_OZ_BOX")) : 1;
+  const int use_ring = (getenv("MCACQ_OZ_RING") != nullptr) ? atoi(getenv("MCACQ_OZ_RING")) : 0;
+  if (one_box && cm_env * cn_env == 1 && !use_ring) dbg |= 4; else dbg &= ~4;
   const uint32_t box_slices = (dbg & 4) ? (uint32_t)G : 1u;
   if ((rc = oz_make_map(&mapA, A_slices, (uint64_t)G, (uint64_t)M, (uint64_t)K, (uint64_t)K, OZ_BM, bk, box_slices))) return rc;
   if ((rc = oz_make_map(&mapB, B_slices, (uint64_t)G, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, bk, box_slices))) return rc;
@@ -870,6 +1072,21 @@ extern "C" int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G
   int tma_store = ((ldc & 1) == 0 && ((uintptr_t)C & 15) == 0) ? 1 : 0;
   if (getenv("MCACQ_OZ_TMASTORE") != nullptr) tma_store = tma_store && atoi(getenv("MCACQ_OZ_TMASTORE"));
   if (tma_store && oz_make_map_c(&mapC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc) != 0) tma_store = 0;
+  // split-ring pipeline (64-byte k-blocks, no clusters): experiment, off by default (slower, see the kernel's comment)
+  if (use_ring && bk == 64 && cm * cn == 1 && (bn == 64 || bn == 80 || bn == 96 || bn == 128)) {
+    const size_t b_bytes = (size_t)2 * G * bn * 64;
+    int NA = (int)((smem_budget - epi_bytes - b_bytes) / (OZ_BM * 64));
+    if (NA > OZ_MAX_NA) NA = OZ_MAX_NA;
+    if (getenv("MCACQ_OZ_NA") != nullptr) { int v = atoi(getenv("MCACQ_OZ_NA")); if (v >= 1 && v < NA) NA = v; }
+    if (NA >= 2) {
+      const size_t smem_ring = b_bytes + (size_t)NA * OZ_BM * 64 + 1024 + epi_bytes;
+      cudaStream_t sr = (cudaStream_t)stream;
+#define OZ_RING_CASE(W) if (bn == W) return oz_launch_ring_t<W>(mapA, mapB, mapC, tma_store, tri_mode, M, N, K, G, NA, smem_ring, \
+                                                                smem_budget, row_scale, col_scale, C, ldc, sr, dbg);
+      OZ_RING_CASE(64) OZ_RING_CASE(80) OZ_RING_CASE(96) OZ_RING_CASE(128)
+#undef OZ_RING_CASE
+    }
+  }
   return oz_launch(bk, bn, cm, cn, mapA, mapB, mapC, tma_store, tri_mode, M, N, K, G, stages, smem, smem_budget, row_scale, col_scale, C, ldc,
                    (cudaStream_t)stream, dbg);
 }

@@ -96,7 +96,7 @@ def contract():
     lines = []
 
     def run(G, env, tri=0):
-        for k in ("MCACQ_OZ_DEBUG", "MCACQ_OZ_STAGES", "MCACQ_OZ_BN", "MCACQ_OZ_BK", "MCACQ_OZ_GROUP", "MCACQ_OZ_HINT", "MCACQ_OZ_TMASTORE"):
+        for k in ("MCACQ_OZ_DEBUG", "MCACQ_OZ_STAGES", "MCACQ_OZ_BN", "MCACQ_OZ_BK", "MCACQ_OZ_GROUP", "MCACQ_OZ_HINT", "MCACQ_OZ_TMASTORE", "MCACQ_OZ_RING", "MCACQ_OZ_NA"):
             os.environ.pop(k, None)
         os.environ.update({k: str(v) for k, v in env.items()})
         As = torch.empty(G, M, n, dtype=torch.int8, device=dev)
@@ -126,6 +126,22 @@ def contract():
         del As, Bs, C
 
     which = sys.argv[2] if len(sys.argv) > 2 else "full"
+    if which == "ring":
+        for G in (4, 5, 6, 7):
+            run(G, {})
+            run(G, {"MCACQ_OZ_RING": 0})
+            run(G, {"MCACQ_OZ_DEBUG": 1})
+            run(G, {"MCACQ_OZ_DEBUG": 2})
+            run(G, {"MCACQ_OZ_NA": 8})
+            run(G, {"MCACQ_OZ_NA": 12})
+            run(G, {"MCACQ_OZ_HINT": 0})
+            run(G, {"MCACQ_OZ_GROUP": 4})
+            run(G, {"MCACQ_OZ_GROUP": 16})
+        for G in (5, 6):
+            run(G, {}, tri=1)
+            run(G, {"MCACQ_OZ_RING": 0}, tri=1)
+        open(f"{OUT}/r02_study_contract_{which}.txt", "w").write("\n".join(lines) + "\n")
+        return
     if which == "epilogue":
         for G in (5, 6, 7):
             run(G, {})
