@@ -48,7 +48,10 @@ class Baseline(C.Structure):
 
 class MC(C.Structure):
     _fields_ = [("S", C.c_int32), ("fat", C.c_int32), ("tau_relu", C.c_double), ("tau_max", C.c_double),
-                ("Zt", C.c_void_p), ("best", C.c_void_p)]
+                ("Zt", C.c_void_p), ("best", C.c_void_p),
+                ("obj_weight", C.c_double), ("obj_offset", C.c_double), ("util_param", C.c_double), ("Zbar", C.c_void_p),
+                ("n_con", C.c_int32), ("con_fat", C.c_int32),
+                ("con_a", C.c_double * 4), ("con_b", C.c_double * 4), ("con_eta", C.c_double * 4)]
 
 
 def build(force: bool = False) -> Path:
@@ -68,6 +71,7 @@ EXPORTS = [
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
+    "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
 ]
 
 
@@ -99,6 +103,11 @@ def lib() -> C.CDLL:
     L.mcacq_workspace_bytes.restype = sz
     L.mcacq_workspace_bytes_model.argtypes = [C.POINTER(Model), i64, i32, i32]
     L.mcacq_workspace_bytes_model.restype = sz
+    L.mcacq_lbfgsb_state_bytes.argtypes = [i64, i32]
+    L.mcacq_lbfgsb_state_bytes.restype = sz
+    L.mcacq_lbfgsb_init.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp]
+    L.mcacq_lbfgsb_step.argtypes = [i64, i32, vp, vp, vp, dbl, vp, vp, dbl, dbl, i32, i32, i32, vp, vp, vp]
+    L.mcacq_lbfgsb_summary.argtypes = [i64, i32, vp, dbl, vp, vp, vp]
     L.mcacq_posterior.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, sz, vp]
     L.mcacq_posterior_backward.argtypes = [C.POINTER(Model), vp, i64, i32, vp, vp, vp, vp, sz, vp]
     L.mcacq_acq_forward.argtypes = [C.POINTER(Model), C.POINTER(Baseline), C.POINTER(MC), vp, i64, i32, vp, vp, vp, sz, vp]
@@ -107,7 +116,7 @@ def lib() -> C.CDLL:
     L.mcacq_log_areas_backward.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mcacq_version", "mcacq_workspace_bytes", "mcacq_workspace_bytes_model"):
+        if name not in ("mcacq_version", "mcacq_workspace_bytes", "mcacq_workspace_bytes_model", "mcacq_lbfgsb_state_bytes"):
             fn.restype = i32
     _lib = L
     return L

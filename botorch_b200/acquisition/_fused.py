@@ -50,12 +50,25 @@ class MCOperands:
     tau_max: float
     fat: bool
     desc: _lib.MC = None
-    mode: int | None = None  # utility mode override (2 qEI/qNEI, 3 qSimpleRegret, 4 qPI); None -> int(fat)
+    mode: int | None = None  # utility mode override (2 qEI/qNEI, 3 qSimpleRegret, 4 qPI, 5 qUCB/qLCB, 6 qPSTD); None -> int(fat)
+    obj_weight: float = 1.0  # affine objective obj = w y + o (LinearMCObjective on the single outcome)
+    obj_offset: float = 0.0
+    util_param: float = 0.0  # modes 5 / 6
+    constraints: tuple = ()  # ((a, b, eta), ...): smoothed indicators of a y + b <= 0
+    con_fat: bool = False
+    Zbar: Tensor = None
 
     def __post_init__(self):
-        self.desc = _lib.MC(S=self.Zt.shape[1], fat=int(self.fat) if self.mode is None else int(self.mode),
-                            tau_relu=float(self.tau_relu),
-                            tau_max=float(self.tau_max), Zt=self.Zt.data_ptr(), best=self.best.data_ptr())
+        mode = int(self.fat) if self.mode is None else int(self.mode)
+        if mode >= 5:
+            self.Zbar = self.Zt.mean(dim=1).contiguous()
+        cons = list(self.constraints)
+        arr = lambda k: (C.c_double * 4)(*([c[k] for c in cons] + [1.0 if k == 2 else 0.0] * (4 - len(cons))))  # noqa: E731
+        self.desc = _lib.MC(S=self.Zt.shape[1], fat=mode, tau_relu=float(self.tau_relu),
+                            tau_max=float(self.tau_max), Zt=self.Zt.data_ptr(), best=self.best.data_ptr(),
+                            obj_weight=float(self.obj_weight), obj_offset=float(self.obj_offset),
+                            util_param=float(self.util_param), Zbar=_lib.ptr(self.Zbar), n_con=len(cons),
+                            con_fat=int(bool(self.con_fat)), con_a=arr(0), con_b=arr(1), con_eta=arr(2))
 
 
 class LaunchStats:
@@ -131,3 +144,35 @@ def fused_acquisition(X: Tensor, strat: DevicePredictionStrategy, base: Baseline
     """acq[b] for X: b x q x d (fp64, CUDA).  Under `torch.no_grad()` no state is kept."""
     acq, _ = FusedMCAcquisition.apply(X, strat, base, mc)
     return acq
+
+
+def affine_constraints(constraints, eta, fat, device=None) -> tuple | None:
+    """Compile outcome constraints for the fused kernels.  The callables are arbitrary Python (reference contract:
+    `sample_shape x batch x q x m` samples -> `sample_shape x batch x q`, feasible iff <= 0), but on a single-outcome
+    model the usual ones are affine in the sample value, `c(y) = a y + b`; those -- at most four, detected by probing the
+    callable -- are evaluated inside `sample_reduce` (smoothed indicator of botorch/utils/objective.py:135-211).  Returns
+    ((a, b, eta), ...) or None when a constraint is not affine / not fusable (the caller then takes the generic route)."""
+    if constraints is None:
+        return ()
+    if len(constraints) > 4 or isinstance(fat, list):
+        return None
+    etas = eta if isinstance(eta, Tensor) else torch.full((len(constraints),), float(eta))
+    if etas.numel() != len(constraints) or not bool((etas > 0).all()):
+        return None
+    probe = torch.tensor([-1.3, 0.0, 2.1, 5.7, -40.0], dtype=torch.float64, device=device).view(1, 1, 5, 1)
+    out = []
+    for con, e in zip(constraints, etas.tolist()):
+        try:
+            c = con(probe)
+        except Exception:  # noqa: BLE001 -- e.g. a callable that indexes a second outcome
+            return None
+        if not isinstance(c, Tensor) or c.shape != probe.shape[:-1]:
+            return None
+        c = c.reshape(-1).to(torch.float64).cpu()
+        y = probe.reshape(-1).cpu()
+        b0 = float(c[1])
+        a0 = float((c[2] - c[1]) / (y[2] - y[1]))
+        if not torch.allclose(c, a0 * y + b0, rtol=1e-12, atol=1e-12):
+            return None
+        out.append((a0, b0, float(e)))
+    return tuple(out)

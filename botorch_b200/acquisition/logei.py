@@ -28,10 +28,10 @@ from ..sampling.get_sampler import get_sampler
 from ..sampling.normal import NormalMCSampler
 from ..utils.safe_math import fatmax, log_fatplus, log_softplus, logmeanexp, smooth_amax
 from ..utils.transforms import concatenate_pending_points, match_batch_shape, t_batch_mode_transform
-from ._fused import BaselineOperands, MCOperands, fused_acquisition
+from ._fused import BaselineOperands, MCOperands, affine_constraints, fused_acquisition
 from .cached_cholesky import CachedCholeskyMCSamplerMixin
 from .monte_carlo import SampleReducingMCAcquisitionFunction
-from .objective import MCAcquisitionObjective, PosteriorTransform
+from .objective import LinearMCObjective, MCAcquisitionObjective, PosteriorTransform
 from .utils import compute_best_feasible_objective, prune_inferior_points
 
 TAU_RELU = 1e-6
@@ -65,10 +65,31 @@ class LogImprovementMCAcquisitionFunction(SampleReducingMCAcquisitionFunction):
 
     # ---- fused-route plumbing -------------------------------------------------------------------
     def _fusable(self, X: Tensor) -> bool:
-        return (isinstance(self.model, SingleTaskGP) and self._identity_objective and self.posterior_transform is None
-                and self._constraints is None and X.is_cuda and X.dtype in (torch.float64, torch.float32)
+        return (isinstance(self.model, SingleTaskGP) and self._affine_objective() is not None
+                and self.posterior_transform is None and self._fused_constraints() is not None
+                and X.is_cuda and X.dtype in (torch.float64, torch.float32)
                 and X.shape[-2] <= _lib.MAX_Q and len(self.sample_shape) == 1
                 and (self.sampler is None or isinstance(self.sampler, NormalMCSampler)))
+
+    def _affine_objective(self) -> tuple[float, float] | None:
+        """(weight, offset) when the objective is affine in the single outcome: `IdentityMCObjective` or a
+        `LinearMCObjective` with one weight (reference objective.py:314-358); None otherwise."""
+        if self._identity_objective:
+            return 1.0, 0.0
+        if isinstance(self.objective, LinearMCObjective) and self.objective.weights.numel() == 1:
+            return float(self.objective.weights.reshape(-1)[0]), 0.0
+        return None
+
+    def _fused_constraints(self) -> tuple | None:
+        if not hasattr(self, "_fused_cons"):
+            self._fused_cons = affine_constraints(self._constraints, self._eta, self._fat,
+                                                  device=self.model.train_inputs[0].device)
+        return self._fused_cons
+
+    def _mc_extras(self) -> dict:
+        w, o = self._affine_objective()
+        return dict(obj_weight=w, obj_offset=o, constraints=self._fused_constraints(), con_fat=bool(self._fat),
+                    mode=self._utility_mode, util_param=float(getattr(self, "_util_param", 0.0)))
 
     def _ensure_sampler(self, probe) -> None:
         if self.sampler is None:
@@ -105,7 +126,7 @@ class qLogExpectedImprovement(LogImprovementMCAcquisitionFunction):
                 raise BotorchError("The fused qLogEI route expects a scalar `best_f`.")
             best = torch.full((S,), float(self.best_f), device=X.device, dtype=torch.float64)
             ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat,
-                             mode=self._utility_mode)
+                             **self._mc_extras())
             self._mc_cache = {key: ops}
         return ops
 
@@ -241,7 +262,7 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
             Zt = self.sampler.base_samples.reshape(S, r + q).t().contiguous()
             best = self._baseline_best_f.reshape(S).to(device=X.device, dtype=torch.float64).contiguous()
             ops = MCOperands(Zt=Zt, best=best, tau_relu=float(self.tau_relu), tau_max=float(self.tau_max), fat=self._fat,
-                             mode=self._utility_mode)
+                             **self._mc_extras())
             self._mc_cache = {key: ops}
         return ops
 

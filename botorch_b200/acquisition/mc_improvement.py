@@ -13,7 +13,6 @@ import torch
 from torch import Tensor
 
 from .logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement
-from .monte_carlo import SampleReducingMCAcquisitionFunction
 
 
 def _use_plain_reductions(acqf) -> None:
@@ -91,15 +90,22 @@ class qNoisyExpectedImprovement(qLogNoisyExpectedImprovement):
         return (obj - self.compute_best_f(obj).unsqueeze(-1)).clamp_min(0)
 
 
-# ---- utilities whose per-sample value depends on the MC mean over ALL samples (no fused mode yet: generic route) ----------
-class qUpperConfidenceBound(SampleReducingMCAcquisitionFunction):
-    """MC-based batch UCB: mean_S max_q (mu + sqrt(beta pi / 2) |y - mu|), mu = MC mean (reference :833-906).  The
-    posterior comes from the CUDA kernels; the utility and reductions are torch ops on the materialised samples."""
+# ---- utilities whose per-sample value depends on the MC mean over ALL samples --------------------------------------------
+# mu_i = mean_s obj[s][i] is linear in the base samples, mu_i = w (mean_i + sum_j coef_ij Zbar_j) + o with Zbar the sample
+# means of the base samples, so the kernels evaluate it in closed form and stay single-pass (utility modes 5 / 6 of
+# `csrc/sample_reduce.cu`); the torch `_sample_forward` below is the generic route (custom objectives, posterior transforms).
+class qUpperConfidenceBound(qLogExpectedImprovement):
+    """MC-based batch UCB: mean_S max_q (mu + sqrt(beta pi / 2) |y - mu|), mu = MC mean (reference :833-906)."""
+
+    _log = False
 
     def __init__(self, model, beta: float, sampler=None, objective=None, posterior_transform=None, X_pending=None) -> None:
-        super().__init__(model=model, sampler=sampler, objective=objective, posterior_transform=posterior_transform,
-                         X_pending=X_pending)
+        super().__init__(model=model, best_f=0.0, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending)
+        _use_plain_reductions(self)
         self.beta_prime = self._get_beta_prime(beta=beta)
+        self._utility_mode = 5
+        self._util_param = self.beta_prime
 
     def _get_beta_prime(self, beta: float) -> float:
         return math.sqrt(beta * math.pi / 2)
@@ -116,14 +122,19 @@ class qLowerConfidenceBound(qUpperConfidenceBound):
         return -super()._get_beta_prime(beta=beta)
 
 
-class qPosteriorStandardDeviation(SampleReducingMCAcquisitionFunction):
+class qPosteriorStandardDeviation(qLogExpectedImprovement):
     """MC-based batch posterior standard deviation: mean_S max_q sqrt(pi / 2) |y - mu| (reference :924-989)."""
+
+    _log = False
 
     def __init__(self, model, sampler=None, objective=None, posterior_transform=None, X_pending=None, constraints=None,
                  eta=1e-3) -> None:
-        super().__init__(model=model, sampler=sampler, objective=objective, posterior_transform=posterior_transform,
-                         X_pending=X_pending, constraints=constraints, eta=eta)
+        super().__init__(model=model, best_f=0.0, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending, constraints=constraints, eta=eta)
+        _use_plain_reductions(self)
         self._scale = math.sqrt(math.pi / 2)
+        self._utility_mode = 6
+        self._util_param = self._scale
 
     def _sample_forward(self, obj: Tensor) -> Tensor:
         mean = obj.mean(dim=0)

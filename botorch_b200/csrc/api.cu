@@ -237,7 +237,10 @@ extern "C" int mcacq_posterior_backward(const mcacq_model* model, const double* 
 static int check_mc(const mcacq_mc* mc) {
   if (!mc || !mc->Zt || !mc->best || mc->S <= 0) return MCACQ_EINVAL;
   if (!(mc->tau_relu > 0.0) || !(mc->tau_max > 0.0)) return MCACQ_EINVAL;
-  if (mc->fat < 0 || mc->fat > 4) return MCACQ_EINVAL;
+  if (mc->fat < 0 || mc->fat > 6) return MCACQ_EINVAL;
+  if ((mc->fat == 5 || mc->fat == 6) && !mc->Zbar) return MCACQ_EINVAL;
+  if (mc->n_con < 0 || mc->n_con > 4) return MCACQ_ELIMIT;
+  for (int k = 0; k < mc->n_con; k++) if (!(mc->con_eta[k] > 0.0)) return MCACQ_EINVAL;
   return 0;
 }
 
@@ -245,6 +248,9 @@ static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc
   const int r = base ? base->r : 0;
   sp.b = b; sp.q = q; sp.r = r; sp.S = mc->S; sp.fat = mc->fat;
   sp.tau_relu = mc->tau_relu; sp.tau_max = mc->tau_max;
+  sp.obj_w = mc->obj_weight; sp.obj_o = mc->obj_offset; sp.util_param = mc->util_param; sp.Zbar = mc->Zbar;
+  sp.n_con = mc->n_con; sp.con_fat = mc->con_fat;
+  for (int k = 0; k < 4; k++) { sp.con_a[k] = mc->con_a[k]; sp.con_b[k] = mc->con_b[k]; sp.con_eta[k] = mc->con_eta[k]; }
   sp.mean = w.mean; sp.Sxx = w.Sxx; sp.Sxb = w.Sxb;
   sp.L_base = r > 0 ? base->L_base : nullptr;
   sp.Zt = mc->Zt; sp.best = mc->best;

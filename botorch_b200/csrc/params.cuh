@@ -57,6 +57,12 @@ struct SRParams {
   double* Cm;            // [b x q x q]
   double* acq;           // [b]
   int32_t* info;         // [b]
+  // round 2: affine objective, MC-mean utilities, smoothed outcome constraints (all optional; see mcacq_mc)
+  double obj_w, obj_o;     // objective = obj_w * y + obj_o
+  double util_param;       // modes 5 / 6: beta' / sqrt(pi / 2)
+  const double* Zbar;      // [(r + q)] mean over the samples of every row of Zt (modes 5 / 6)
+  int n_con, con_fat;
+  double con_a[4], con_b[4], con_eta[4];
   // backward only
   const double* grad_acq;  // [b]
   double* gmean;           // [b*q]

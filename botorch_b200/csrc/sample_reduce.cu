@@ -93,6 +93,62 @@ __device__ __forceinline__ double log_improve(double z, double tau, double inv_t
   }
 }
 
+
+// ---- smoothed feasibility of one sample value (botorch/utils/objective.py:135-211) -----------------------------------
+// log sigmoid(u) / log fatmoid(u) and its derivative with respect to u.
+__device__ __forceinline__ double log_feas_term(double u, int fat, double& dlf) {
+  if (fat) {
+    // fatmoid (safe_math.py:441-458): u < 0: 2/3 cauchy(u - 1/sqrt3), else 1 - 2/3 cauchy(u + 1/sqrt3)
+    const double c3 = 0.57735026918962576451;
+    if (u < 0.0) {
+      const double a = u - c3, den = fma(a, a, 1.0);
+      dlf = -2.0 * a / den;
+      return log((2.0 / 3.0) / den);
+    }
+    const double bb = u + c3, den = fma(bb, bb, 1.0);
+    const double fv = 1.0 - (2.0 / 3.0) / den;
+    dlf = ((4.0 / 3.0) * bb / (den * den)) / fv;
+    return log(fv);
+  }
+  // logexpit(u) = -log1pexp(-u) (safe_math.py:96-98, 78-93: log1p(exp(x)) for x <= 18, x + exp(-x) above)
+  const double x = -u;
+  double l1p, sig;   // log1pexp(x), sigmoid(x) = d log1pexp / dx
+  if (x <= 18.0) { const double e = exp(x); l1p = log1p(e); sig = e / (1.0 + e); }
+  else { const double e = exp(-x); l1p = x + e; sig = 1.0 - e; }
+  dlf = sig;         // d(-log1pexp(-u)) / du = sigmoid(-u)
+  return -l1p;
+}
+
+// Per-sample, per-point utility of a posterior sample value y: objective (affine), utility mode, constraint weighting.
+// dy = d val / d y,  dm = d val / d mu_i (modes 5 / 6: mu_i = MC mean of the objective).
+template <bool GRAD>
+__device__ __forceinline__ double sr_element(const SRParams& p, double yi, double bst, double mu, double inv_tau_relu,
+                                             double& dy, double& dm) {
+  const double obj = fma(p.obj_w, yi, p.obj_o);
+  double val, dobj = 0.0;
+  dm = 0.0;
+  if (p.fat >= 5) {
+    const double dev = obj - mu;
+    const double sgn = (dev > 0.0) ? 1.0 : ((dev < 0.0) ? -1.0 : 0.0);
+    val = ((p.fat == 5) ? mu : 0.0) + p.util_param * fabs(dev);
+    if (GRAD) { dobj = p.util_param * sgn; dm = ((p.fat == 5) ? 1.0 : 0.0) - p.util_param * sgn; }
+  } else {
+    val = log_improve<GRAD>(obj - bst, p.tau_relu, inv_tau_relu, p.fat, dobj);
+  }
+  dy = dobj * p.obj_w;
+  if (p.n_con > 0) {
+    double lf = 0.0, dlf = 0.0;
+    for (int k = 0; k < p.n_con; k++) {
+      double dk;
+      lf += log_feas_term(-(fma(p.con_a[k], yi, p.con_b[k])) / p.con_eta[k], p.con_fat, dk);
+      dlf += dk * (-p.con_a[k] / p.con_eta[k]);
+    }
+    if (p.fat <= 1) { val += lf; dy += dlf; }          // log family: add the log-indicator (monte_carlo.py:322-348)
+    else { const double F = exp(lf); dy = dy * F + val * F * dlf; dm *= F; val *= F; }
+  }
+  return val;
+}
+
 // q-reduction: fatmax (fat) or smooth_amax; optionally the weights d fm / d li_i.
 template <int QMAX, bool GRAD>
 __device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, double tau, double inv_tau, int fat,
@@ -196,7 +252,8 @@ sample_reduce_fwd_kernel(SRParams p) {
                                                     //  which must not alias T or the jitter retries would re-read garbage)
   double* smean = Tm + q * q;                  // [q]
   double* red = smean + q;                     // [2 * SR_WARPS]
-  double* fmv = red + 2 * SR_WARPS;            // [S] per-sample utilities (W > 1 only)
+  double* smu = red + 2 * SR_WARPS;            // [q] MC mean of the objective (utility modes 5 / 6)
+  double* fmv = smu + q;                       // [S] per-sample utilities (W > 1 only)
   __shared__ int s_info;
   __shared__ int s_nonfinite;
 
@@ -285,6 +342,15 @@ sample_reduce_fwd_kernel(SRParams p) {
   }
   __syncthreads();
 
+  // MC mean of the objective per point in closed form: obj_w (mean_i + sum_j coef_ij Zbar_j) + obj_o
+  if (p.fat >= 5) {
+    for (int i = tid; i < q; i += NT) {
+      double m = smean[i];
+      for (int j = 0; j < r + q; j++) m = fma(coefT[j * QP + i], p.Zbar[j], m);
+      smu[i] = fma(p.obj_w, m, p.obj_o);
+    }
+  }
+  __syncthreads();
   // ---- samples: NS samples per thread, coefficients broadcast from shared memory
   const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
   double lm = -CUDART_INF, ls = 0.0;
@@ -315,8 +381,8 @@ sample_reduce_fwd_kernel(SRParams p) {
         if (i < q) {
           const double yi = y[i] + smean[i];
           if (!isfinite(yi)) nonfinite = true;
-          double dl;
-          li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
+          double dl, dmm;
+          li[i] = sr_element<false>(p, yi, bst, (p.fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
         } else li[i] = -CUDART_INF;
       }
       fmv[s0] = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
@@ -366,8 +432,8 @@ sample_reduce_fwd_kernel(SRParams p) {
             if (i < q) {
               const double yi = y[ns][i] + smean[i];
               if (!isfinite(yi)) nonfinite = true;
-              double dl;
-              li[i] = log_improve<false>(yi - bst, p.tau_relu, inv_tau_relu, p.fat, dl);
+              double dl, dmm;
+              li[i] = sr_element<false>(p, yi, bst, (p.fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
             } else li[i] = -CUDART_INF;
           }
           const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
@@ -426,6 +492,9 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   const int GP = q | 1;                        // odd pitch for the weight rows
   double* gy = mats + 4 * q * q;               // [chunk + 3][GP]  per-sample weights (zero padded to a multiple of 4 rows)
   double* stage = gy + (size_t)(chunk + 4) * GP;  // [SR_WARPS][QMAX][8] cross-warp staging of DMMA partials
+  double* smu = stage + (size_t)SR_WARPS * QMAX * 8;   // [q] MC mean of the objective (modes 5 / 6)
+  double* sam = smu + q;                               // [q] sum_s d acq / d mu_i
+  double* gy2 = sam + q;                               // [chunk + 4][GP] per-sample d acq / d mu_i (modes 5 / 6 only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t bb = blockIdx.x;
 
@@ -446,6 +515,16 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   const double gout = p.grad_acq[bb];
   const double lse_total = p.acq[bb] + log((double)S);
   const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
+  const bool mc_mean = p.fat >= 5;
+  if (mc_mean) {
+    for (int i = tid; i < q; i += NT) {
+      double m = smean[i];
+      for (int j = 0; j < r + q; j++) m = fma(coefT[j * QP + i], p.Zbar[j], m);
+      smu[i] = fma(p.obj_w, m, p.obj_o);
+      sam[i] = 0.0;
+    }
+    __syncthreads();
+  }
 
 
 
@@ -480,11 +559,11 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
       for (int ns = 0; ns < NS; ns++) {
         if (s0 + ns < cend) {
           const double bst = p.best[s0 + ns];
-          double li[QMAX], dli[QMAX], w[QMAX];
+          double li[QMAX], dli[QMAX], dmu[QMAX], w[QMAX];
 #pragma unroll
           for (int i = 0; i < QMAX; i++) {
-            if (i < q) li[i] = log_improve<true>(y[ns][i] + smean[i] - bst, p.tau_relu, inv_tau_relu, p.fat, dli[i]);
-            else { li[i] = -CUDART_INF; dli[i] = 0.0; }
+            if (i < q) li[i] = sr_element<true>(p, y[ns][i] + smean[i], bst, mc_mean ? smu[i] : 0.0, inv_tau_relu, dli[i], dmu[i]);
+            else { li[i] = -CUDART_INF; dli[i] = 0.0; dmu[i] = 0.0; }
           }
           const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, inv_tau_max, p.fat, w);
           double ws;
@@ -494,6 +573,11 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           double* gys = gy + (size_t)(s0 + ns - c0) * GP;
 #pragma unroll
           for (int i = 0; i < QMAX; i++) if (i < q) gys[i] = ws * w[i] * dli[i];
+          if (mc_mean) {
+            double* gms = gy2 + (size_t)(s0 + ns - c0) * GP;
+#pragma unroll
+            for (int i = 0; i < QMAX; i++) if (i < q) gms[i] = ws * w[i] * dmu[i];
+          }
         }
       }
     }
@@ -564,9 +648,31 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
         }
         __syncthreads();
       }
+      if (mc_mean) {
+        // sum over the chunk's samples of d acq / d mu_i: the first 4 warps take the points, lanes stride over the samples
+        // (the same split for every W, so wide and narrow launches agree bit for bit)
+        if (warp < SR_WARPS) {
+          for (int i = warp; i < q; i += SR_WARPS) {
+            double a = 0.0;
+            for (int sl = lane; sl < nloc; sl += 32) a += gy2[(size_t)sl * GP + i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) sam[i] += a;
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   __syncthreads();
+  if (mc_mean) {
+    // mu_i = obj_w (mean_i + sum_j coef_ij Zbar_j) + obj_o feeds back into the mean and into every coefficient
+    for (int idx = tid; idx < q * NC; idx += NT) {
+      const int i = idx / NC, j = idx - i * NC;
+      gco[idx] += p.obj_w * sam[i] * ((j < r + q) ? p.Zbar[j] : 1.0);
+    }
+    __syncthreads();
+  }
 
   // ---- Cholesky reverse-mode (warp 0): gT = sym( L^{-T} Phi(L^T gL) L^{-1} )
   double* Lm = mats;
@@ -643,7 +749,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
 static size_t fwd_smem(int q, int r, int S, int wide) {
   int QP = (q + 1) & ~1;
   size_t scratch = (size_t)q * (r > q ? r : q);
-  return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS + (wide ? (size_t)S : 0)) * sizeof(double);
+  return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS + q + (wide ? (size_t)S : 0)) * sizeof(double);
 }
 
 // q-batches below which the wide (4 x 128 threads) variants are used: fewer CTAs than the machine has SM sub-partitions
@@ -653,11 +759,11 @@ static bool sr_use_wide(int64_t b) {
   return e != nullptr ? atoi(e) != 0 : b < SR_WIDE_BELOW;
 }
 
-static size_t bwd_smem(int q, int r, int chunk, int qmax) {
+static size_t bwd_smem(int q, int r, int chunk, int qmax, bool mc_mean) {
   int QP = (q + 1) & ~1;
   int GP = q | 1;
   return ((size_t)(r + q) * QP + (size_t)q * (r + q + 1) + q + 4 * (size_t)q * q + (size_t)(chunk + 4) * GP +
-          (size_t)SR_WARPS * qmax * 8) * sizeof(double);
+          (size_t)SR_WARPS * qmax * 8 + 2 * (size_t)q + (mc_mean ? (size_t)(chunk + 4) * GP : 0)) * sizeof(double);
 }
 
 template <int QMAX, int NS, int W>
@@ -675,12 +781,13 @@ static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
 template <int QMAX, int NS, int W>
 static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
-  int chunk = (36 * 1024) / (8 * (p.q | 1));
+  const bool mc_mean = p.fat >= 5;
+  int chunk = ((mc_mean ? 18 : 36) * 1024) / (8 * (p.q | 1));
   if (chunk > p.S) chunk = p.S;
   chunk = (chunk / (SR_THREADS * NS)) * (SR_THREADS * NS);
   if (chunk < SR_THREADS * NS) chunk = SR_THREADS * NS;
   if ((int64_t)chunk * (p.q | 1) < (int64_t)p.q * p.r) chunk = (p.q * p.r + (p.q | 1) - 1) / (p.q | 1);
-  size_t smem = bwd_smem(p.q, p.r, chunk, QMAX);
+  size_t smem = bwd_smem(p.q, p.r, chunk, QMAX, mc_mean);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
   auto kern = sample_reduce_bwd_kernel<QMAX, NS, W>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

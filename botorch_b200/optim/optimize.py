@@ -11,6 +11,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
+from .. import settings
 from ..exceptions.errors import UnsupportedError
 from ..exceptions.warnings import OptimizationWarning
 from .initializers import gen_batch_initial_conditions
@@ -50,7 +51,12 @@ def _optimize_acqf_batch(acq_function, bounds: Tensor, q: int, num_restarts: int
     """reference :364-620 (box-bounded part: no feasibility projection)."""
     from ..generation.gen import gen_candidates_scipy  # local import: generation <-> optim are mutually dependent
 
-    gen_candidates = gen_candidates_scipy if gen_candidates is None else gen_candidates
+    if gen_candidates is None:
+        gen_candidates = gen_candidates_scipy
+        if settings.optimizer.value() == "device" and bounds.is_cuda:
+            from ..generation.device_gen import gen_candidates_device
+
+            gen_candidates = gen_candidates_device
     ic_generator = gen_batch_initial_conditions if ic_generator is None else ic_generator
     sharded = shard_across_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     provided = batch_initial_conditions

@@ -9,6 +9,12 @@ is executed:
               1e-7 of the FP64 contraction; a model that no slice count serves runs on "dmma"
               (`DevicePredictionStrategy._select_int8`).  ~2x faster than "dmma".  This is the default.
 `int8_slices` = (g_fwd, g_bwd) pins the slice counts and skips the probe (benchmarks / developer tools only).
+
+`optimizer` selects what `optimize_acqf` uses when no `gen_candidates` is passed:
+  * "scipy"  -- `gen_candidates_scipy`: scipy's own L-BFGS-B routine stepped on the host (iterates bit-identical to
+                `scipy.optimize.minimize` per restart, as in the reference), one fused forward+backward per round;
+  * "device" -- `gen_candidates_device`: the same algorithm with the state machines resident on the GPU and one CUDA graph
+                replay per round (no host hop); candidates agree with "scipy" to optimiser tolerance, not bit for bit.
 """
 from __future__ import annotations
 
@@ -41,3 +47,4 @@ class _Flag:
 
 contraction = _Flag("int8")
 int8_slices = _Flag(None)
+optimizer = _Flag("scipy")

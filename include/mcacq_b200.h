@@ -103,11 +103,30 @@ typedef struct {
   int32_t S;           /* number of MC samples                                              */
   int32_t fat;         /* utility mode: 1 log_fatplus+fatmax+logmeanexp (qLogEI/qLogNEI), 0 log_softplus+smooth_amax+
                         * logmeanexp, 2 relu+amax+mean (qEI/qNEI), 3 identity+amax+mean (qSimpleRegret),
-                        * 4 sigmoid((y-best)/tau_relu)+amax+mean (qProbabilityOfImprovement)  */
+                        * 4 sigmoid((y-best)/tau_relu)+amax+mean (qProbabilityOfImprovement), 5 / 6 see util_param */
   double tau_relu;
   double tau_max;
   const double* Zt;    /* [(r + q) x S] base samples, TRANSPOSED (sample index contiguous)  */
   const double* best;  /* [S] per-sample incumbent (qLogEI: best_f repeated)                */
+  /* Affine objective on the (single) outcome: obj = obj_weight * y + obj_offset -- `LinearMCObjective` on an m = 1 model
+   * (botorch/acquisition/objective.py:318-358); 1, 0 = `IdentityMCObjective`.                                           */
+  double obj_weight;
+  double obj_offset;
+  /* Utility modes whose per-sample value uses the MC mean mu_i = mean_s obj[s][i] (botorch/acquisition/monte_carlo.py):
+   *   5  mu + util_param |obj - mu|, amax, mean   (qUpperConfidenceBound :896-906, util_param = sqrt(beta pi / 2);
+   *                                                qLowerConfidenceBound :909-921 with the negative root)
+   *   6  util_param |obj - mu|, amax, mean        (qPosteriorStandardDeviation :979-989, util_param = sqrt(pi / 2))
+   * mu_i is evaluated in closed form, obj_weight (mean_i + sum_j coef_ij Zbar_j) + obj_offset, Zbar = row means of Zt.   */
+  double util_param;
+  const double* Zbar;  /* [(r + q)] (modes 5 / 6 only)                                                                   */
+  /* Smoothed outcome constraints `c_k(y) = con_a[k] y + con_b[k] <= 0` (compute_smoothed_feasibility_indicator,
+   * botorch/utils/objective.py:135-211): the per-sample utility is weighted by prod_k sigmoid(-c_k / con_eta[k]) (added as
+   * log-sigmoid in the log modes 0 / 1); con_fat = 1 uses the fat-tailed `fatmoid` (safe_math.py:441-458).              */
+  int32_t n_con;       /* 0 .. 4                                                                                         */
+  int32_t con_fat;
+  double con_a[4];
+  double con_b[4];
+  double con_eta[4];
 } mcacq_mc;
 
 const char* mcacq_version(void);
@@ -212,6 +231,28 @@ int mcacq_log_areas_backward(const void* grad_out, const void* obj_subsets, cons
  * caller).  Replaces the host draw + the H2D copy of `raw_samples x q x d` doubles per `optimize_acqf` call.           */
 int mcacq_sobol_draw(const int64_t* sobolstate, const int64_t* shift, int dim, int64_t n, int64_t first_index, double* out,
                      void* stream);
+
+/* ---- device-resident batched L-BFGS-B (csrc/lbfgsb.cu) ---------------------------------------
+ * Replaces the host loop of botorch/optim/batched_lbfgs_b.py:365-634 (`fmin_l_bfgs_b_batched`: one scipy `setulb` state
+ * machine per restart, all active restarts evaluated together) and the numpy <-> device hop of
+ * botorch/generation/gen.py:423-485 (`f_np_wrapper`).  N independent problems of dimension D (= q * d), shared box
+ * [lower, upper] (length D; +-inf = unbounded), history m = 10.  Reverse communication through device buffers:
+ *   mcacq_lbfgsb_init   clamps x0 into X [N x D] and resets the state;
+ *   mcacq_lbfgsb_step   consumes f [N] and g [N x D] evaluated at X (the optimiser MINIMISES sign * f, so sign = -1 feeds
+ *                       acquisition values and their gradients directly), advances every still-active problem to its next
+ *                       trial point, written into X, and counts the active problems into *n_active (device int, optional);
+ *                       finished problems keep their final iterate in X;
+ *   mcacq_lbfgsb_summary f [N] (sign removed) and status [N x 4] = (task, message, iterations, evaluations);
+ *                       task: 0 active, 2 converged, 3 stopped (iteration / evaluation limit), 4 abnormal line search;
+ *                       message: scipy's task word (401 pgtol, 402 factr, 502 maxfun, 504 maxiter).
+ * factr / pgtol / maxiter / maxfun / maxls as in scipy (`ftol = factr * eps`).                                         */
+size_t mcacq_lbfgsb_state_bytes(int64_t N, int D);
+int mcacq_lbfgsb_init(int64_t N, int D, const double* x0, const double* lower, const double* upper, double* X, void* state,
+                      void* stream);
+int mcacq_lbfgsb_step(int64_t N, int D, double* X, const double* f, const double* g, double sign, const double* lower,
+                      const double* upper, double factr, double pgtol, int maxiter, int maxfun, int maxls, void* state,
+                      int32_t* n_active, void* stream);
+int mcacq_lbfgsb_summary(int64_t N, int D, const void* state, double sign, double* f, int32_t* status, void* stream);
 
 /* Number of kernels the last forward/backward call on this thread launched (for bench accounting). */
 int mcacq_last_launch_count(void);

@@ -49,4 +49,5 @@ def _restore_settings():
     saved = (settings.contraction.value(), settings.int8_slices.value())
     yield
     settings.contraction.set(saved[0])
+    settings.optimizer.set("scipy")
     settings.int8_slices.set(saved[1])
