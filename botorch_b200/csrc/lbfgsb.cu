@@ -26,6 +26,7 @@ constexpr int LB_THREADS = 128;
 constexpr int LB_WARPS = LB_THREADS / 32;
 constexpr int LB_M = 10;        // history length (scipy default `maxcor`)
 constexpr int LB_2M = 2 * LB_M;
+constexpr int LB_P = LB_2M + 1;  // odd pitch of the dense 2m x 2m matrices: lane = row accesses are bank-conflict free
 
 enum { LB_FG = 0, LB_NEW_X = 1, LB_CONVERGED = 2, LB_STOPPED = 3, LB_ABNORMAL = 4 };
 enum { LB_PH_START = 0, LB_PH_LINESEARCH = 1 };
@@ -125,40 +126,53 @@ __device__ __forceinline__ void lb_multi_dot(int K, int D, double* out, F term) 
   __syncthreads();
 }
 
-// ---- dense (<= 20 x 20) LU with partial pivoting, thread 0 ---------------------------------------------------------------
-// Factorises A (row-major, pitch LB_2M) in place; piv[i] = row swapped into position i.  Returns false on a zero pivot.
-__device__ bool lb_lu_factor(double* A, int* piv, int k) {
+// ---- dense (<= 20 x 20) LU with partial pivoting, warp 0 (all 32 lanes), operands in shared memory ----------------------
+// Factorises A (row-major, pitch LB_2M) in place, LAPACK style (whole rows are interchanged); piv[i] = row swapped into
+// position i.  Lane = row during the elimination, lane = column during the interchange.  Returns false on a zero pivot.
+__device__ bool lb_lu_factor_w(double* A, int* piv, int k) {
+  const int lane = threadIdx.x & 31;
   for (int i = 0; i < k; i++) {
-    int p = i;
-    double best = fabs(A[i * LB_2M + i]);
-    for (int r = i + 1; r < k; r++) {
-      const double a = fabs(A[r * LB_2M + i]);
-      if (a > best) { best = a; p = r; }
+    double a = (lane >= i && lane < k) ? fabs(A[lane * LB_P + i]) : -1.0;
+    int idx = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // largest magnitude, lowest row on ties (first maximum)
+      const double a2 = __shfl_xor_sync(0xffffffffu, a, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (a2 > a || (a2 == a && i2 < idx)) { a = a2; idx = i2; }
     }
-    if (!(best > 0.0)) return false;
-    piv[i] = p;
-    if (p != i)
-      for (int c = 0; c < k; c++) { const double tmp = A[i * LB_2M + c]; A[i * LB_2M + c] = A[p * LB_2M + c]; A[p * LB_2M + c] = tmp; }
-    for (int r = i + 1; r < k; r++) {
-      const double fct = A[r * LB_2M + i] / A[i * LB_2M + i];
-      A[r * LB_2M + i] = fct;
-      for (int c = i + 1; c < k; c++) A[r * LB_2M + c] -= fct * A[i * LB_2M + c];
+    if (!(a > 0.0)) return false;
+    if (lane == 0) piv[i] = idx;
+    if (idx != i && lane < k) { const double tmp = A[i * LB_P + lane]; A[i * LB_P + lane] = A[idx * LB_P + lane]; A[idx * LB_P + lane] = tmp; }
+    __syncwarp();
+    if (lane > i && lane < k) {
+      const double fct = A[lane * LB_P + i] / A[i * LB_P + i];
+      A[lane * LB_P + i] = fct;
+      for (int c = i + 1; c < k; c++) A[lane * LB_P + c] -= fct * A[i * LB_P + c];
     }
+    __syncwarp();
   }
   return true;
 }
-__device__ void lb_lu_solve(const double* LU, const int* piv, int k, const double* b, double* x) {
-  double y[LB_2M];
-  for (int i = 0; i < k; i++) y[i] = b[i];
+// x = A^{-1} b from the factors (b, x, ys: shared memory; ys is scratch of LB_2M doubles).  All interchanges are applied to
+// the right-hand side first, then the unit-lower and the upper solve run column by column (lane = row).
+__device__ void lb_lu_solve_w(const double* LU, const int* piv, int k, const double* b, double* x, double* ys) {
+  const int lane = threadIdx.x & 31;
+  if (lane < k) ys[lane] = b[lane];
+  __syncwarp();
+  if (lane == 0)
+    for (int i = 0; i < k; i++) { const int p = piv[i]; if (p != i) { const double tmp = ys[i]; ys[i] = ys[p]; ys[p] = tmp; } }
+  __syncwarp();
   for (int i = 0; i < k; i++) {
-    const int p = piv[i];
-    if (p != i) { const double tmp = y[i]; y[i] = y[p]; y[p] = tmp; }
-    for (int r = i + 1; r < k; r++) y[r] -= LU[r * LB_2M + i] * y[i];
+    const double yi = ys[i];
+    if (lane > i && lane < k) ys[lane] -= LU[lane * LB_P + i] * yi;
+    __syncwarp();
   }
-  for (int i = k - 1; i >= 0; i--) {
-    double s = y[i];
-    for (int c = i + 1; c < k; c++) s -= LU[i * LB_2M + c] * x[c];
-    x[i] = s / LU[i * LB_2M + i];
+  for (int c = k - 1; c >= 0; c--) {
+    if (lane == c) x[c] = ys[c] / LU[c * LB_P + c];
+    __syncwarp();
+    const double xc = x[c];
+    if (lane < c) ys[lane] -= LU[lane * LB_P + c] * xc;
+    __syncwarp();
   }
 }
 
@@ -297,10 +311,10 @@ struct LbShared {
   double sc[S_NSCALARS];
   int is[I_NINTS];
   double SS[LB_M * LB_M], SY[LB_M * LB_M];
-  double Minv[LB_2M * LB_2M];   // LU of M^{-1}
-  double K3[LB_2M * LB_2M];
+  double Minv[LB_2M * LB_P];   // LU of M^{-1}
+  double K3[LB_2M * LB_P];
   int pivM[LB_2M], pivK[LB_2M];
-  double p[LB_2M], c[LB_2M], v[LB_2M], wbp[LB_2M], mc[LB_2M], rhs[LB_2M];
+  double p[LB_2M], c[LB_2M], v[LB_2M], wbp[LB_2M], mc[LB_2M], rhs[LB_2M], ys[LB_2M];
   double dots[LB_2M * (LB_2M + 1) / 2 + LB_2M];
   double bc[8];   // broadcast scalars
   int bi[8];
@@ -320,36 +334,46 @@ __device__ double lb_projgr(int D, const double* x, const double* g, const doubl
   return lb_block_max(mx, red);
 }
 
-// builds LU(M^{-1}) in sh.Minv from SS / SY / theta; returns false when singular.  All threads call; thread 0 works.
+// M^{-1}[a][b] of the compact representation from S'S, S'Y and theta
+__device__ __forceinline__ double lb_minv_entry(const LbShared& sh, int c, double theta, int a, int b) {
+  if (a < c && b < c) return (a == b) ? -sh.SY[a * LB_M + a] : 0.0;
+  if (a < c) return ((b - c) > a) ? sh.SY[(b - c) * LB_M + a] : 0.0;          // L^T[a][b-c] = L[b-c][a], b-c > a
+  if (b < c) return ((a - c) > b) ? sh.SY[(a - c) * LB_M + b] : 0.0;          // L[a-c][b], strictly lower
+  return theta * sh.SS[(a - c) * LB_M + (b - c)];
+}
+
+// builds LU(M^{-1}) in sh.Minv; returns false when singular.  All threads call.
 __device__ bool lb_factor_minv(LbShared& sh, int c, double theta) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int k = 2 * c;
-    for (int a = 0; a < k; a++)
-      for (int b = 0; b < k; b++) {
-        double v;
-        if (a < c && b < c) v = (a == b) ? -sh.SY[a * LB_M + a] : 0.0;
-        else if (a < c) v = ((b - c) > a) ? sh.SY[(b - c) * LB_M + a] : 0.0;          // L^T[a][b-c] = L[b-c][a], b-c > a
-        else if (b < c) v = ((a - c) > b) ? sh.SY[(a - c) * LB_M + b] : 0.0;          // L[a-c][b], strictly lower
-        else v = theta * sh.SS[(a - c) * LB_M + (b - c)];
-        sh.Minv[a * LB_2M + b] = v;
-      }
-    sh.bi[0] = lb_lu_factor(sh.Minv, sh.pivM, k) ? 1 : 0;
+  const int k = 2 * c;
+  for (int e = threadIdx.x; e < k * k; e += LB_THREADS) {
+    const int a = e / k, b = e - a * k;
+    sh.Minv[a * LB_P + b] = lb_minv_entry(sh, c, theta, a, b);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool ok = lb_lu_factor_w(sh.Minv, sh.pivM, k);
+    if (threadIdx.x == 0) sh.bi[0] = ok ? 1 : 0;
   }
   __syncthreads();
   return sh.bi[0] != 0;
 }
 
-// W[j][i] of the compact representation: j < c -> Y_j[i], else theta * S_{j-c}[i]
-__device__ __forceinline__ double lb_W(const double* S, const double* Y, size_t Dp, int head, int c, double theta, int j, int i) {
+// W[j][i] of the compact representation: j < c -> Y_j[i], else theta * S_{j-c}[i].  `Wsm` != nullptr: the 2c x D matrix has
+// been staged in shared memory for this iteration (every element is read 2c + 3 times by the Cauchy / subspace steps, and
+// the 2c (2c + 1) / 2 masked Gram dot products are latency-bound when each operand is an L2 access).
+__device__ __forceinline__ double lb_W(const double* S, const double* Y, size_t Dp, int head, int c, double theta, int j, int i,
+                                       const double* Wsm = nullptr) {
+  if (Wsm != nullptr) return Wsm[(size_t)j * Dp + i];
   return (j < c) ? Y[(size_t)lb_row(head, j) * Dp + i] : theta * S[(size_t)lb_row(head, j - c) * Dp + i];
 }
 
 __global__ void __launch_bounds__(LB_THREADS)
 lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict__ f_in, const double* __restrict__ g_in,
                    const double* __restrict__ lower, const double* __restrict__ upper, double* __restrict__ state, LbParams prm,
-                   int32_t* __restrict__ n_active) {
+                   int32_t* __restrict__ n_active, int stage_w) {
   __shared__ LbShared sh;
+  extern __shared__ __align__(16) double lb_dyn[];   // [2 m][Dp] staged W (when it fits: stage_w != 0)
   const int64_t b = blockIdx.x;
   const int D = L.D, tid = threadIdx.x;
   const size_t Dp = (size_t)((D + 1) & ~1);
@@ -504,6 +528,15 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
       ok = true;
       const int c = sh.is[I_COL], head = sh.is[I_HEAD];
       const double theta = sh.sc[S_THETA];
+      const double* Wsm = nullptr;
+      if (stage_w && c > 0) {
+        for (int e = tid; e < 2 * c * D; e += LB_THREADS) {
+          const int j = e / D, i = e - j * D;
+          lb_dyn[(size_t)j * Dp + i] = lb_W(S, Y, Dp, head, c, theta, j, i);
+        }
+        Wsm = lb_dyn;
+        __syncthreads();
+      }
       int nb = 0;
       double pf1 = 0.0;
       for (int i = tid; i < D; i += LB_THREADS) {
@@ -521,15 +554,15 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
       const int nbreak = (int)(lb_block_sum((double)nb, sh.red) + 0.5);
       // p = W dC
       if (c > 0) {
-        lb_multi_dot(2 * c, D, sh.p, [&](int k, int i) { return lb_W(S, Y, Dp, head, c, theta, k, i) * dC[i]; });
+        lb_multi_dot(2 * c, D, sh.p, [&](int k, int i) { return lb_W(S, Y, Dp, head, c, theta, k, i, Wsm) * dC[i]; });
         if (!lb_factor_minv(sh, c, theta)) { ok = false; }
       }
       if (ok) {
+        if (tid < 32 && c > 0) lb_lu_solve_w(sh.Minv, sh.pivM, 2 * c, sh.p, sh.v, sh.ys);
         if (tid == 0) {
           double f1 = f1_0, f2 = -theta * f1;
           for (int k = 0; k < 2 * c; k++) sh.c[k] = 0.0;
           if (c > 0) {
-            lb_lu_solve(sh.Minv, sh.pivM, 2 * c, sh.p, sh.v);
             double pv = 0.0;
             for (int k = 0; k < 2 * c; k++) pv += sh.p[k] * sh.v[k];
             f2 -= pv;
@@ -549,38 +582,51 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
           const double dt = tj - sh.bc[5];
           if (sh.bc[3] < dt) break;
           // consume the breakpoint
-          if (c > 0 && tid < 2 * c) sh.wbp[tid] = lb_W(S, Y, Dp, head, c, theta, tid, bidx);
+          if (c > 0 && tid < 2 * c) sh.wbp[tid] = lb_W(S, Y, Dp, head, c, theta, tid, bidx, Wsm);
           __syncthreads();
-          if (tid == 0) {
-            double f1 = sh.bc[0], f2 = sh.bc[1], dtm = sh.bc[3];
-            sh.bc[4] += dt;
-            const double dibp = dC[bidx];
-            dC[bidx] = 0.0;
-            double zibp;
-            if (dibp > 0.0) { zibp = u[bidx] - x[bidx]; xcp[bidx] = u[bidx]; }
-            else { zibp = l[bidx] - x[bidx]; xcp[bidx] = l[bidx]; }
-            freem[bidx] = 0.0;
-            tbreak[bidx] = CUDART_INF_F;
-            if (kbp == nbreak - 1 && nbreak == D) {
-              dtm = dt; sh.bi[2] = 1;
-            } else {
-              const double dibp2 = dibp * dibp;
-              f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
-              f2 = f2 - theta * dibp2;
-              if (c > 0) {
-                for (int k = 0; k < 2 * c; k++) sh.c[k] += dt * sh.p[k];
-                lb_lu_solve(sh.Minv, sh.pivM, 2 * c, sh.wbp, sh.v);
-                double wmc = 0.0, wmp = 0.0, wmw = 0.0;
-                for (int k = 0; k < 2 * c; k++) { wmc += sh.c[k] * sh.v[k]; wmp += sh.p[k] * sh.v[k]; wmw += sh.wbp[k] * sh.v[k]; }
-                for (int k = 0; k < 2 * c; k++) sh.p[k] -= dibp * sh.wbp[k];
-                f1 += dibp * wmc;
-                f2 += 2.0 * dibp * wmp - dibp2 * wmw;
-              }
-              f2 = fmax(DBL_EPSILON * sh.bc[2], f2);
-              dtm = -f1 / f2;
-              sh.bc[5] = tj;
+          if (tid < 32) {
+            // lane 0 moves the variable to its bound; the 2c-sized algebra (c += dt p, v = M wbp) runs on the warp
+            if (tid == 0) {
+              sh.bc[4] += dt;
+              const double dibp = dC[bidx];
+              dC[bidx] = 0.0;
+              double zibp;
+              if (dibp > 0.0) { zibp = u[bidx] - x[bidx]; xcp[bidx] = u[bidx]; }
+              else { zibp = l[bidx] - x[bidx]; xcp[bidx] = l[bidx]; }
+              freem[bidx] = 0.0;
+              tbreak[bidx] = CUDART_INF_F;
+              sh.bc[6] = dibp; sh.bc[7] = zibp;
+              sh.bi[2] = (kbp == nbreak - 1 && nbreak == D) ? 1 : 0;
             }
-            sh.bc[0] = f1; sh.bc[1] = f2; sh.bc[3] = dtm;
+            __syncwarp();
+            const bool last = sh.bi[2] != 0;
+            if (!last && c > 0) {
+              if (tid < 2 * c) sh.c[tid] += dt * sh.p[tid];
+              __syncwarp();
+              lb_lu_solve_w(sh.Minv, sh.pivM, 2 * c, sh.wbp, sh.v, sh.ys);
+            }
+            if (tid == 0) {
+              double f1 = sh.bc[0], f2 = sh.bc[1], dtm = sh.bc[3];
+              const double dibp = sh.bc[6], zibp = sh.bc[7];
+              if (last) {
+                dtm = dt;
+              } else {
+                const double dibp2 = dibp * dibp;
+                f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
+                f2 = f2 - theta * dibp2;
+                if (c > 0) {
+                  double wmc = 0.0, wmp = 0.0, wmw = 0.0;
+                  for (int k = 0; k < 2 * c; k++) { wmc += sh.c[k] * sh.v[k]; wmp += sh.p[k] * sh.v[k]; wmw += sh.wbp[k] * sh.v[k]; }
+                  for (int k = 0; k < 2 * c; k++) sh.p[k] -= dibp * sh.wbp[k];
+                  f1 += dibp * wmc;
+                  f2 += 2.0 * dibp * wmp - dibp2 * wmw;
+                }
+                f2 = fmax(DBL_EPSILON * sh.bc[2], f2);
+                dtm = -f1 / f2;
+                sh.bc[5] = tj;
+              }
+              sh.bc[0] = f1; sh.bc[1] = f2; sh.bc[3] = dtm;
+            }
           }
           __syncthreads();
           if (sh.bi[2]) break;
@@ -599,14 +645,14 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
         for (int i = tid; i < D; i += LB_THREADS) pnf += freem[i];
         const int nfree = (int)(lb_block_sum(pnf, sh.red) + 0.5);
         if (nfree > 0 && c > 0) {
-          if (tid == 0) lb_lu_solve(sh.Minv, sh.pivM, 2 * c, sh.c, sh.mc);
+          if (tid < 32) lb_lu_solve_w(sh.Minv, sh.pivM, 2 * c, sh.c, sh.mc, sh.ys);
           __syncthreads();
           // r (into wk1, zero on fixed variables)
           for (int i = tid; i < D; i += LB_THREADS) {
             double r = 0.0;
             if (freem[i] != 0.0) {
               double wm = 0.0;
-              for (int k = 0; k < 2 * c; k++) wm += lb_W(S, Y, Dp, head, c, theta, k, i) * sh.mc[k];
+              for (int k = 0; k < 2 * c; k++) wm += lb_W(S, Y, Dp, head, c, theta, k, i, Wsm) * sh.mc[k];
               r = -theta * (xcp[i] - x[i]) - g[i] + wm;
             }
             wk1[i] = r;
@@ -616,32 +662,25 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
           const int k2 = 2 * c, npair = k2 * (k2 + 1) / 2;
           lb_multi_dot(npair + k2, D, sh.dots, [&](int k, int i) {
             if (freem[i] == 0.0) return 0.0;
-            if (k >= npair) return lb_W(S, Y, Dp, head, c, theta, k - npair, i) * wk1[i];
+            if (k >= npair) return lb_W(S, Y, Dp, head, c, theta, k - npair, i, Wsm) * wk1[i];
             int a = 0, rem = k;   // k -> (a, bcol) with a <= bcol, rows of length k2 - a
             while (rem >= k2 - a) { rem -= k2 - a; a++; }
             const int bcol = a + rem;
-            return lb_W(S, Y, Dp, head, c, theta, a, i) * lb_W(S, Y, Dp, head, c, theta, bcol, i);
+            return lb_W(S, Y, Dp, head, c, theta, a, i, Wsm) * lb_W(S, Y, Dp, head, c, theta, bcol, i, Wsm);
           });
-          if (tid == 0) {
-            // K3 = M^{-1} - Wz Wz^T / theta: rebuild M^{-1} (sh.Minv holds its LU)
-            int kk = 0;
-            for (int a = 0; a < k2; a++)
-              for (int bcol = a; bcol < k2; bcol++, kk++) {
-                const double wv = sh.dots[kk] / theta;
-                sh.K3[a * LB_2M + bcol] = -wv; sh.K3[bcol * LB_2M + a] = -wv;
-              }
-            for (int a = 0; a < k2; a++)
-              for (int bcol = 0; bcol < k2; bcol++) {
-                double v;
-                if (a < c && bcol < c) v = (a == bcol) ? -sh.SY[a * LB_M + a] : 0.0;
-                else if (a < c) v = ((bcol - c) > a) ? sh.SY[(bcol - c) * LB_M + a] : 0.0;
-                else if (bcol < c) v = ((a - c) > bcol) ? sh.SY[(a - c) * LB_M + bcol] : 0.0;
-                else v = theta * sh.SS[(a - c) * LB_M + (bcol - c)];
-                sh.K3[a * LB_2M + bcol] += v;
-              }
-            for (int a = 0; a < k2; a++) sh.rhs[a] = sh.dots[npair + a];
-            if (lb_lu_factor(sh.K3, sh.pivK, k2)) { lb_lu_solve(sh.K3, sh.pivK, k2, sh.rhs, sh.v); sh.bi[3] = 1; }
-            else sh.bi[3] = 0;
+          // K3 = M^{-1} - Wz Wz^T / theta (sh.Minv holds the LU of M^{-1}, so its entries are rebuilt)
+          for (int e = tid; e < k2 * k2; e += LB_THREADS) {
+            const int a = e / k2, bcol = e - a * k2;
+            const int lo = a < bcol ? a : bcol, hi = a < bcol ? bcol : a;
+            const int kk = lo * k2 - lo * (lo - 1) / 2 + (hi - lo);   // index of (lo, hi) in the packed upper triangle
+            sh.K3[a * LB_P + bcol] = lb_minv_entry(sh, c, theta, a, bcol) - sh.dots[kk] / theta;
+          }
+          if (tid < k2) sh.rhs[tid] = sh.dots[npair + tid];
+          __syncthreads();
+          if (tid < 32) {
+            const bool okf = lb_lu_factor_w(sh.K3, sh.pivK, k2);
+            if (okf) lb_lu_solve_w(sh.K3, sh.pivK, k2, sh.rhs, sh.v, sh.ys);
+            if (tid == 0) sh.bi[3] = okf ? 1 : 0;
           }
           __syncthreads();
           if (!sh.bi[3]) ok = false;
@@ -653,7 +692,7 @@ lbfgsb_step_kernel(LbLayout L, double* __restrict__ X, const double* __restrict_
               double xb = xcp[i];
               if (freem[i] != 0.0) {
                 double wv = 0.0;
-                for (int k = 0; k < k2; k++) wv += lb_W(S, Y, Dp, head, c, theta, k, i) * sh.v[k];
+                for (int k = 0; k < k2; k++) wv += lb_W(S, Y, Dp, head, c, theta, k, i, Wsm) * sh.v[k];
                 const double dF = (wk1[i] + wv / theta) / theta;
                 wk1[i] = dF;
                 xb = fmin(fmax(xcp[i] + dF, l[i]), u[i]);
@@ -813,8 +852,17 @@ extern "C" int mcacq_lbfgsb_step(int64_t N, int D, double* X, const double* f, c
     cudaError_t e = cudaMemsetAsync(n_active, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
-  lbfgsb_step_kernel<<<(unsigned)N, LB_THREADS, 0, (cudaStream_t)stream>>>(lb_layout(N, D), X, f, g, lower, upper, (double*)state,
-                                                                             prm, n_active);
+  // W = [Y, theta S] (2 m x D) staged in shared memory per iteration when it fits next to the static working set
+  const size_t w_bytes = (size_t)LB_2M * (size_t)((D + 1) & ~1) * sizeof(double);
+  const int stage_w = w_bytes <= 160 * 1024 ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(lbfgsb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  lbfgsb_step_kernel<<<(unsigned)N, LB_THREADS, stage_w ? w_bytes : 0, (cudaStream_t)stream>>>(
+      lb_layout(N, D), X, f, g, lower, upper, (double*)state, prm, n_active, stage_w);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

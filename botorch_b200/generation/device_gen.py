@@ -57,9 +57,15 @@ class DeviceLBFGSB:
         self.X = torch.empty(self.N, self.D, **f64)
         self.state = torch.zeros(L.mcacq_lbfgsb_state_bytes(self.N, self.D), dtype=torch.uint8, device=dev)
         self.n_active = torch.zeros(1, dtype=torch.int32, device=dev)
-        x0c = x0.to(**f64).contiguous()
-        _lib.check(L.mcacq_lbfgsb_init(self.N, self.D, x0c.data_ptr(), self.lower.data_ptr(), self.upper.data_ptr(),
-                                       self.X.data_ptr(), self.state.data_ptr(), _lib.stream_ptr()), "mcacq_lbfgsb_init")
+        self.reset(x0)
+
+    def reset(self, x0: Tensor) -> None:
+        """Restart all N problems from `x0` (clamped into the box); buffers and their addresses stay the same."""
+        x0c = x0.to(device=self.X.device, dtype=torch.float64).contiguous()
+        _lib.check(_lib.lib().mcacq_lbfgsb_init(self.N, self.D, x0c.data_ptr(), self.lower.data_ptr(), self.upper.data_ptr(),
+                                                self.X.data_ptr(), self.state.data_ptr(), _lib.stream_ptr()),
+                   "mcacq_lbfgsb_init")
+        self.n_active.fill_(self.N)
 
     def step(self, f: Tensor, g: Tensor, sign: float = 1.0) -> None:
         """Feed f [N], g [N x D] evaluated at `self.X`; `self.X` then holds the next trial points."""
@@ -104,6 +110,7 @@ class _FusedRound:
         self.stats = LaunchStats
         self.graph = None
         self.launches_per_round = 0
+        self.use_graph = use_graph
         self._launch()             # warm-up outside capture (first-call attribute / occupancy queries, tensor-map encoder)
         self.rounds = 1
         if use_graph:
@@ -134,6 +141,12 @@ class _FusedRound:
         o.step(self.acq, self.gX.view(N, -1), sign=-1.0)
         self.launches_per_round = n1 + n2 + 2
 
+    def restart(self, x0: Tensor) -> None:
+        """Re-use the captured round for a new set of initial conditions (same shapes, same operands, same options)."""
+        self.opt.reset(x0)
+        self.info_or.zero_()
+        self.rounds = 0
+
     def run(self) -> None:
         if self.graph is not None:
             self.graph.replay()
@@ -141,6 +154,26 @@ class _FusedRound:
             self._launch()
         self.rounds += 1
         self.stats.launches += self.launches_per_round
+
+
+def _cached_round(acqf, opt: DeviceLBFGSB, clamped: Tensor, q: int, d: int, options: dict) -> _FusedRound:
+    """Capturing a round costs milliseconds, an optimiser round 0.1-1 ms: the captured graph (with its static buffers and
+    optimiser state) is kept on the acquisition function and re-used by later calls with the same shapes, operands and
+    L-BFGS-B options (sequential greedy optimisation, retries, repeated `optimize_acqf` calls)."""
+    use_graph = bool(options.get("cuda_graph", True))
+    strat = acqf.model.prediction_strategy()
+    base = acqf._baseline_operands() if hasattr(acqf, "_baseline_operands") else None
+    mc = acqf._mc_operands(opt.X.view(opt.N, q, d))
+    key = (opt.N, q, d, opt.maxiter, opt.maxfun, opt.factr, opt.pgtol, opt.maxls, use_graph, id(strat), id(base), id(mc),
+           tuple(opt.lower.tolist()), tuple(opt.upper.tolist()))
+    cache = acqf.__dict__.setdefault("_device_rounds", {})
+    rnd = cache.get(key)
+    if rnd is not None and rnd.strat is strat and rnd.base is base and rnd.mc is mc:
+        rnd.restart(clamped.reshape(opt.N, q * d))
+        return rnd
+    cache.clear()   # one live graph per acquisition function (each holds a workspace)
+    rnd = cache[key] = _FusedRound(acqf, opt, q, d, use_graph=use_graph)
+    return rnd
 
 
 def _fused_capable(acqf, X: Tensor) -> bool:
@@ -184,7 +217,8 @@ def gen_candidates_device(initial_conditions: Tensor, acquisition_function, lowe
     timed_out = False
     Xv = opt.X.view(nb, q, d)
     if _fused_capable(acquisition_function, Xv):
-        rnd = _FusedRound(acquisition_function, opt, q, d, use_graph=bool(options.get("cuda_graph", True)))
+        rnd = _cached_round(acquisition_function, opt, clamped, q, d, options)
+        opt = rnd.opt
         done = rnd.rounds
         while done < max_rounds:
             rnd.run()

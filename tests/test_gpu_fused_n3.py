@@ -80,24 +80,38 @@ def test_affine_outcome_constraints_inside_the_kernel(fat):
     spec, data, model, X = _setup(S=128)
     med = float(data.train_Y.median())
     cons = [lambda Y: Y[..., 0] - (med + 0.4), lambda Y: -2.0 * Y[..., 0] + 2.0 * (med - 1.5)]   # med - 1.5 <= y <= med + 0.4
-    # an opaque (but equal) restatement keeps the second acquisition function on the generic route
-    opaque = [lambda Y: (Y[..., 0] - (med + 0.4)) + 0.0 * Y[..., 0] ** 2 + 0.0 * torch.sin(Y[..., 0]),
-              lambda Y: -2.0 * Y[..., 0] + 2.0 * (med - 1.5) + 0.0 * Y[..., 0].abs().sqrt()]
+    # the reference arm: the same constraints behind an objective the fused route does not recognise (generic torch route)
+    from botorch_b200.acquisition.objective import GenericMCObjective
+
+    ident = lambda: GenericMCObjective(lambda Y, X=None: Y[..., 0])  # noqa: E731
     eta = torch.tensor([2e-2, 5e-2])
     best = torch.tensor(med - 0.3, dtype=torch.float64, device=DEV)
     kw = dict(eta=eta, fat=fat)
     f = qLogExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=cons, **kw)
-    g = qLogExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=opaque, **kw)
-    assert f._fused_constraints() and g._fused_constraints() is None
+    g = qLogExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=cons, objective=ident(), **kw)
+    assert len(f._fused_constraints()) == 2 and not g._fusable(X)
+    a0, b0, e0 = f._fused_constraints()[0]
+    assert abs(a0 - 1.0) < 1e-12 and abs(b0 + (med + 0.4)) < 1e-12 and abs(e0 - 2e-2) < 1e-9
     _same(f, g, X)
     Xb = data.X_baseline.to(DEV)
-    _same(qLogNoisyExpectedImprovement(model, X_baseline=Xb, sampler=_sampler(128), constraints=cons, prune_baseline=False, **kw),
-          qLogNoisyExpectedImprovement(model, X_baseline=Xb, sampler=_sampler(128), constraints=opaque, prune_baseline=False, **kw), X)
+
+    def nei(**extra):
+        # every baseline point violates the first constraint, so `best_f` is the reference's 6-sigma lower bound over 32
+        # UNSEEDED uniform points (acquisition/utils.py:181-219): seed the global generator so that both arms draw the same
+        torch.manual_seed(11)
+        return qLogNoisyExpectedImprovement(model, X_baseline=Xb, sampler=_sampler(128), constraints=cons,
+                                            prune_baseline=False, **kw, **extra)
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # "When all training points are infeasible ..."
+        _same(nei(), nei(objective=ident()), X)
     if not fat:   # the non-log family multiplies by the plain sigmoid indicator
         _same(qExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=cons, eta=eta),
-              qExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=opaque, eta=eta), X)
+              qExpectedImprovement(model, best_f=best, sampler=_sampler(128), constraints=cons, eta=eta, objective=ident()), X)
         _same(qPosteriorStandardDeviation(model, sampler=_sampler(128), constraints=cons, eta=eta),
-              qPosteriorStandardDeviation(model, sampler=_sampler(128), constraints=opaque, eta=eta), X)
+              qPosteriorStandardDeviation(model, sampler=_sampler(128), constraints=cons, eta=eta, objective=ident()), X)
 
 
 def test_non_affine_or_probabilistic_constraints_take_the_generic_route():
@@ -133,7 +147,6 @@ def test_mc_mean_utilities_fused_vs_generic_and_reference_formula(w):
     Xc = X.cpu()
     mean, cov = orc.gp.posterior_mvn(Xc)
     Lq = torch.linalg.cholesky(cov)
-    Z = _sampler(256)._draw_for_test(256, spec.q) if hasattr(_sampler(256), "_draw_for_test") else None
     acqf = qUpperConfidenceBound(model, beta=2.0, sampler=_sampler(256), objective=lin)
     v = acqf(X)
     Z = acqf.sampler.base_samples.reshape(256, spec.q).cpu()
