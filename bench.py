@@ -371,7 +371,8 @@ def main():
                     "traffic_source": "ncu dram__bytes_read+write at M=16384 scaled to this M (profiles/README.md)"}
 
         def int8_roofline():
-            G = 6
+            st8 = head["model"].prediction_strategy() if args.contraction == "int8" else alt["model"].prediction_strategy()
+            G = int(st8.g_fwd) if st8.contraction == "int8" else 7   # the slice count the build-time probe picked for THIS model
             pairs = G * (G + 1) // 2
             A = torch.rand(M, strat.np, **f64)
             sl = torch.empty(G, M, strat.np, dtype=torch.int8, device=dev)
@@ -407,15 +408,16 @@ def main():
             # roofline of THIS algorithm on the INT8 tensor pipe: every fp64 multiply-add costs G(G+1)/2 int8 multiply-adds;
             # dense int8 peak of the part = 2 x the measured dense bf16 peak
             peak_equiv = 2.0 * bf16_peak / pairs
-            return {"bound": "tensor", "kernel": "ozaki_imma_kernel (tcgen05 kind::i8, G=6 forward launch)", "achieved": ach,
-                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.59e9 * (M / 65536.0),
+            return {"bound": "tensor", "kernel": f"ozaki_imma_kernel (tcgen05 kind::i8, G={G} forward launch)", "achieved": ach,
+                    "slices_fwd_bwd": [int(st8.g_fwd), int(st8.g_bwd)], "mode_in_effect": st8.contraction,
+                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.59e9 * (M / 65536.0) * (G / 6.0),
                     "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
                     "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
                     "library_int8_gemm_tops_measured": lib_int8,
                     "frac_of_library_int8_gemm": (ach * pairs / lib_int8) if lib_int8 else None,
                     "fp64_dgemm_peak_measured": fp64_peak_tf,
-                    "traffic_source": "ncu --set full dram__bytes_read+write of the forward launch at M=65536 (6.47 + 2.12 GB, "
-                                      "profiles/r01_ncu_full_int8_mode.md; algorithmic: 1.7 GB slices + 2.15 GB output), scaled to this M"}
+                    "traffic_source": "ncu --set full dram__bytes_read+write of the G=6 forward launch at M=65536 (6.47 + 2.12 GB, "
+                                      "profiles/r01_ncu_full_int8_mode.md; algorithmic: 1.7 GB slices + 2.15 GB output), scaled to this M and G"}
 
         roof = {"int8": int8_roofline, "dmma": dmma_roofline}
         roofline = roof[args.contraction]()
@@ -433,9 +435,11 @@ def main():
                 "config": {"workload": workload, "chunk_q_batches": chunk, "per_gpu_q_batches": b_local,
                            "l2": "inputs larger than L2 (per-chunk working set %.1f GB)" % (2 * chunk * spec.q * model.prediction_strategy().np * 8 / 1e9),
                            "parallelism": f"shard b over {world} GPU(s), all-gather of values",
-                           "contraction": ("int8: Ozaki split of the fp64 contraction onto the INT8 tensor cores (tcgen05), "
-                                           "6/5 diagonals of signed 8-bit slices, parity-tested at 1e-9" if args.contraction == "int8"
-                                           else "dmma: FP64 DMMA tensor-core kernel")},
+                           "contraction": (("int8 (library default): Ozaki split of the fp64 contraction onto the INT8 tensor cores "
+                                            "(tcgen05); %d forward / %d backward signed 8-bit slices picked by the per-model "
+                                            "probe at the training points (variance within 2.5e-10 of the FP64 contraction)"
+                                            % (model.prediction_strategy().g_fwd, model.prediction_strategy().g_bwd))
+                                           if model.prediction_strategy().contraction == "int8" else "dmma: FP64 DMMA tensor-core kernel")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
                         "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "phases": head["phases"],

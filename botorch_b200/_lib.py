@@ -20,6 +20,7 @@ KERNEL_RBF = 0
 KERNEL_MATERN52 = 1
 TRI_UPPER, TRI_LOWER, TRI_DENSE = 0, 1, 2
 INFO_JITTER_MASK, INFO_NOT_PSD, INFO_NONFINITE = 0x7, 0x8, 0x10
+INFO_FLAG_MASK, INFO_COND_SHIFT, INFO_COND_MASK = 0x1F, 8, 0xFF00
 MAX_Q, MAX_D, MAX_R = 32, 64, 64
 
 _ERRORS = {-1: "MCACQ_EINVAL (bad argument)", -2: "MCACQ_ELIMIT (q/r/d/S outside compiled limits)",
@@ -51,7 +52,8 @@ class MC(C.Structure):
                 ("Zt", C.c_void_p), ("best", C.c_void_p),
                 ("obj_weight", C.c_double), ("obj_offset", C.c_double), ("util_param", C.c_double), ("Zbar", C.c_void_p),
                 ("n_con", C.c_int32), ("con_fat", C.c_int32),
-                ("con_a", C.c_double * 4), ("con_b", C.c_double * 4), ("con_eta", C.c_double * 4)]
+                ("con_a", C.c_double * 4), ("con_b", C.c_double * 4), ("con_eta", C.c_double * 4),
+                ("jitter_f32", C.c_int32), ("_pad", C.c_int32)]
 
 
 def build(force: bool = False) -> Path:
@@ -71,7 +73,7 @@ EXPORTS = [
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
-    "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
+    "mcacq_sample_reduce_forward", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
 ]
 
 
@@ -103,6 +105,7 @@ def lib() -> C.CDLL:
     L.mcacq_workspace_bytes.restype = sz
     L.mcacq_workspace_bytes_model.argtypes = [C.POINTER(Model), i64, i32, i32]
     L.mcacq_workspace_bytes_model.restype = sz
+    L.mcacq_sample_reduce_forward.argtypes = [C.POINTER(Baseline), C.POINTER(MC), vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_lbfgsb_state_bytes.argtypes = [i64, i32]
     L.mcacq_lbfgsb_state_bytes.restype = sz
     L.mcacq_lbfgsb_init.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp]

@@ -68,7 +68,8 @@ class MCOperands:
                             tau_max=float(self.tau_max), Zt=self.Zt.data_ptr(), best=self.best.data_ptr(),
                             obj_weight=float(self.obj_weight), obj_offset=float(self.obj_offset),
                             util_param=float(self.util_param), Zbar=_lib.ptr(self.Zbar), n_con=len(cons),
-                            con_fat=int(bool(self.con_fat)), con_a=arr(0), con_b=arr(1), con_eta=arr(2))
+                            con_fat=int(bool(self.con_fat)), con_a=arr(0), con_b=arr(1), con_eta=arr(2),
+                            jitter_f32=int(torch.get_default_dtype() == torch.float32), _pad=0)
 
 
 class LaunchStats:
@@ -81,20 +82,37 @@ class LaunchStats:
         cls.launches += int(_lib.lib().mcacq_last_launch_count())
 
 
-def _raise_on_info(info: Tensor) -> None:
+def _info_summary(info: Tensor) -> tuple[int, int]:
+    """(OR-free summary of the status words, one device synchronisation): largest flag part and largest conditioning byte."""
+    if not info.numel():
+        return 0, 0
+    # flag bits: all non-negative bit sets, max == 0 <=> all clear; conditioning byte: bits 8..15 (monotone in the word)
+    flags, top = torch.stack([(info & _lib.INFO_FLAG_MASK).max(), info.max()]).tolist()
+    return int(flags), (int(top) & _lib.INFO_COND_MASK) >> _lib.INFO_COND_SHIFT
+
+
+def _raise_on_info(info: Tensor, flags: int | None = None) -> None:
     """Mirror the reference's numerical signalling: NumericalWarning on jitter (psd_safe_cholesky),
     NotPSDError after 6 tries, NanError on non-finite samples (utils/low_rank.py:162-171)."""
-    flags = int(info.max().item()) if info.numel() else 0  # all status words are non-negative bit sets: max == 0 <=> all clear
+    if flags is None:
+        flags = _info_summary(info)[0]
     if flags == 0:
         return
-    host = info.cpu()
+    host = info.cpu() & _lib.INFO_FLAG_MASK
     if bool(((host & _lib.INFO_NOT_PSD) != 0).any()):
         raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up to 1.0e-03.")
     if bool(((host & _lib.INFO_NONFINITE) != 0).any()):
         raise NanError("Samples contain nans or infs.")
-    lvl = int((host & _lib.INFO_JITTER_MASK).max())
-    if lvl > 0:
-        warnings.warn(f"A not p.d., added jitter of {1e-8 * 10 ** (lvl - 1):.1e} to the diagonal", NumericalWarning)
+    # one warning per escalation level that occurred, in the order psd_safe_cholesky would have emitted them for the batch
+    # (it warns once per retry round: every level up to the largest needed by any element)
+    levels = sorted(set((host & _lib.INFO_JITTER_MASK).tolist()) - {0})
+    if levels:
+        counts = {lv: int(((host & _lib.INFO_JITTER_MASK) == lv).sum()) for lv in levels}
+        for lv in range(1, levels[-1] + 1):
+            n_here = counts.get(lv, 0)
+            warnings.warn(f"A not p.d., added jitter of {1e-8 * 10 ** (lv - 1):.1e} to the diagonal"
+                          + (f" ({n_here} of {host.numel()} q-batches became p.d. at this level)" if n_here else ""),
+                          NumericalWarning)
 
 
 class FusedMCAcquisition(torch.autograd.Function):
@@ -113,7 +131,6 @@ class FusedMCAcquisition(torch.autograd.Function):
                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "mcacq_acq_forward")
         LaunchStats.add()
-        _raise_on_info(info)
         ctx.strat, ctx.base, ctx.mc = strat, base, mc
         ctx.ws = ws
         ctx.save_for_backward(Xc, acq)
@@ -139,10 +156,52 @@ class FusedMCAcquisition(torch.autograd.Function):
         return gX, None, None, None
 
 
+class _DropRows(torch.autograd.Function):
+    """Identity whose backward zeroes the gradient rows of the q-batches that were re-evaluated elsewhere (their int8
+    gradient rows are unused, and may be non-finite if the fixed-point blocks happened not to be positive definite)."""
+
+    @staticmethod
+    def forward(ctx, X: Tensor, holder: dict):
+        ctx.holder = holder
+        return X.view_as(X)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        idx = ctx.holder.get("idx")
+        return (g if idx is None else g.index_fill(0, idx, 0.0)), None
+
+
+class RerouteStats:
+    """How many q-batches the int8 mode sent to the FP64 contraction because of their conditioning (diagnostics / tests)."""
+
+    q_batches = 0
+    calls = 0
+
+
 def fused_acquisition(X: Tensor, strat: DevicePredictionStrategy, base: BaselineOperands | None,
                       mc: MCOperands) -> Tensor:
-    """acq[b] for X: b x q x d (fp64, CUDA).  Under `torch.no_grad()` no state is kept."""
-    acq, _ = FusedMCAcquisition.apply(X, strat, base, mc)
+    """acq[b] for X: b x q x d (fp64, CUDA).  Under `torch.no_grad()` no state is kept.
+
+    int8 contraction mode: the fixed-point contraction reproduces the posterior blocks to an ABSOLUTE accuracy (a fraction of
+    the prior variance, which `DevicePredictionStrategy._select_int8` bounds per fitted model), and a q-batch whose joint
+    covariance is nearly singular amplifies any absolute perturbation by 1 / rho (rho = smallest relative Cholesky pivot,
+    reported per q-batch in the status word).  q-batches beyond `strat.int8_cond_limit` are therefore re-evaluated -- value
+    and gradient -- through the FP64 DMMA contraction, so that the mode's accuracy does not depend on where X lies."""
+    limit = strat.int8_cond_limit if strat.contraction == "int8" else None
+    holder = {}
+    X8 = _DropRows.apply(X, holder) if (limit is not None and X.requires_grad and torch.is_grad_enabled()) else X
+    acq, info = FusedMCAcquisition.apply(X8, strat, base, mc)
+    flags, cond = _info_summary(info)
+    if limit is not None and cond > limit:
+        idx = ((info >> _lib.INFO_COND_SHIFT) & 0xFF).gt(limit).nonzero().squeeze(-1)
+        holder["idx"] = idx
+        acq64, info64 = FusedMCAcquisition.apply(X.index_select(0, idx), strat.fp64_view(), base, mc)
+        acq = acq.index_copy(0, idx, acq64)       # the int8 results of these q-batches (and their gradient path) are dropped
+        info = info.index_copy(0, idx, info64)
+        RerouteStats.q_batches += int(idx.numel())
+        RerouteStats.calls += 1
+        flags = _info_summary(info)[0]
+    _raise_on_info(info, flags)
     return acq
 
 

@@ -38,6 +38,7 @@ int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 struct Workspace {
   double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale, *mean_part,
       *A_absmax;
+  int32_t* slice_exp;
   int8_t* slices;
   int32_t* counter;
   size_t bytes;
@@ -74,6 +75,7 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int i
   // operands of the optional INT8 contraction: 6 slices of the M x np left operand + its row scales
   w.slice_scale = (double*)take((size_t)M * 8);
   w.A_absmax = (double*)take((size_t)M * 8);
+  w.slice_exp = (int32_t*)take((size_t)M * 4);
   w.mean_part = (double*)take(int8_g ? (size_t)((np + 63) / 64) * M * 8 : 256);
   w.slices = (int8_t*)take(int8_g ? (size_t)int8_g * M * np : 256);
   w.bytes = off;
@@ -199,7 +201,7 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   // int8 mode: the kernel emits the slices of dA (scaled by a per-row bound) instead of the fp64 matrix
   const bool fuse_slices = (model->contraction == 1) && (r == 0 || base->A_base_absmax != nullptr);
   bp.emit_slices = fuse_slices ? 1 : 0; bp.G = model->g_bwd;
-  bp.slices = w.slices; bp.slice_scale = w.slice_scale; bp.A_absmax = w.A_absmax;
+  bp.slices = w.slices; bp.slice_scale = w.slice_scale; bp.slice_exp = w.slice_exp; bp.A_absmax = w.A_absmax;
   bp.Ab_absmax = r > 0 ? base->A_base_absmax : nullptr;
   if ((rc = posterior_blocks_bwd(bp, st))) return rc;
   if (model->contraction == 1) {
@@ -249,7 +251,7 @@ static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc
   sp.b = b; sp.q = q; sp.r = r; sp.S = mc->S; sp.fat = mc->fat;
   sp.tau_relu = mc->tau_relu; sp.tau_max = mc->tau_max;
   sp.obj_w = mc->obj_weight; sp.obj_o = mc->obj_offset; sp.util_param = mc->util_param; sp.Zbar = mc->Zbar;
-  sp.n_con = mc->n_con; sp.con_fat = mc->con_fat;
+  sp.n_con = mc->n_con; sp.con_fat = mc->con_fat; sp.jitter_f32 = mc->jitter_f32;
   for (int k = 0; k < 4; k++) { sp.con_a[k] = mc->con_a[k]; sp.con_b[k] = mc->con_b[k]; sp.con_eta[k] = mc->con_eta[k]; }
   sp.mean = w.mean; sp.Sxx = w.Sxx; sp.Sxb = w.Sxb;
   sp.L_base = r > 0 ? base->L_base : nullptr;
@@ -309,4 +311,27 @@ extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline
   if ((rc = sample_reduce_bwd(sp, st))) return rc;
 
   return run_posterior_backward(model, base, b, q, w.gmean, w.gSxx, w.gSxb, w, grad_X, st);
+}
+
+// Sample / reduce stage alone on caller-provided posterior blocks (mean, Sxx, Sxb on the original outcome scale): what
+// `sample_cached_cholesky` + `_sample_forward` + the q- and sample reductions compute once the posterior is known.  Lets
+// tests drive `psd_safe_cholesky`'s jitter ladder with covariance blocks of a KNOWN escalation level.
+extern "C" int mcacq_sample_reduce_forward(const mcacq_baseline* base, const mcacq_mc* mc, const double* mean, const double* Sxx,
+                                           const double* Sxb, int64_t b, int q, double* acq, int32_t* info, double* Bm,
+                                           double* Cm, void* stream) {
+  int rc = check_mc(mc);
+  if (rc) return rc;
+  if (b < 0 || q <= 0) return MCACQ_EINVAL;
+  if (b == 0) return 0;
+  const int r = base ? base->r : 0;
+  if (r < 0 || !mean || !Sxx || !acq || !info || !Cm || (r > 0 && (!Sxb || !Bm || !base->L_base))) return MCACQ_EINVAL;
+  if (q > MCACQ_MAX_Q || r > MCACQ_MAX_R) return MCACQ_ELIMIT;
+  g_launch_count = 0;
+  SRParams sp;
+  Workspace w = {};
+  w.mean = const_cast<double*>(mean); w.Sxx = const_cast<double*>(Sxx); w.Sxb = const_cast<double*>(Sxb);
+  w.Bm = Bm; w.Cm = Cm;
+  fill_sr(sp, base, mc, b, q, w);
+  sp.acq = acq; sp.info = info;
+  return sample_reduce_fwd(sp, (cudaStream_t)stream);
 }

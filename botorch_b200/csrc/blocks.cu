@@ -11,6 +11,8 @@
 // as 32-byte per-thread vectors: lane (g, t) holds row g, columns k0+4t..k0+4t+3, and the four
 // consecutive DMMA steps use a k-permutation (virtual k = (step, t) <-> actual k0 + 4t + step) that is
 // applied identically to both operands, so no shared-memory staging or shuffles are needed.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "params.cuh"
 
@@ -267,7 +269,14 @@ posterior_blocks_kernel(BlocksParams p) {
 // written IN PLACE over A, row_scale[i] = s * gmean[i] (the rank-1 mean term is applied by the covariance
 // backward kernel), and the direct kernel terms of K(X, X) and K(X, X_base) into dU.
 
-template <int QT, int RT>
+//
+// int8 mode (emit_slices): the G signed 8-bit slices of dA are emitted instead of the fp64 matrix, each row in fixed point
+// relative to a power of two above its largest entry.  PASS = 1 computes that largest entry (the same DMMA sequence, no
+// stores; atomicMax of the exponent over the column chunks of a row), PASS = 2 emits the slices with it.  Scaling by the
+// ACTUAL row maximum matters: the a-priori bound sum_j |C[i][j]| max|A[j][:]| (PASS = 0, kept behind MCACQ_DA_BOUND=1)
+// overestimates rows whose terms cancel -- nearly collinear rows of A with alternating coefficients, i.e. exactly the
+// ill-conditioned q-batches -- by the inverse of the smallest relative pivot, and every factor 256 costs one slice.
+template <int QT, int RT, int PASS>
 __global__ void __launch_bounds__(BLK_WARPS * 32)
 posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -305,7 +314,20 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
 
   // int8 mode: exponent of an upper bound of |dA[i][:]| <= sum_j |C[i][j]| max|A[j][:]| + sum_j' |Cb[i][j']| max|A_base[j'][:]|
   int shift[QT];
-  if (p.emit_slices) {
+  double rowmax[QT];
+#pragma unroll
+  for (int mi = 0; mi < QT; mi++) { shift[mi] = 0; rowmax[mi] = 0.0; }
+  if (PASS == 2) {
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      const int i = mi * 8 + g;
+      int ex = (i < q) ? p.slice_exp[bb * q + i] : 0;
+      if (ex < -2000) ex = 0;   // an all-zero (or non-finite) row: every digit is zero whatever the scale
+      shift[mi] = 8 * p.G - 2 - ex;
+      if (t4 == 0 && i < q && chunk == 0) p.slice_scale[bb * q + i] = ldexp(1.0, ex + 2);
+    }
+  }
+  if (PASS == 0 && p.emit_slices) {
 #pragma unroll
     for (int mi = 0; mi < QT; mi++) {
       double bnd = 0.0;
@@ -372,12 +394,20 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
     // any lane overwrites them in place
     __syncwarp();
     const int oc = c0 + 2 * NT * t4;
+    if (PASS == 1) {
+      // columns beyond col_end were loaded as zeros, rows beyond q have zero coefficients: their accumulators are 0
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) rowmax[mi] = fmax(rowmax[mi], fmax(fabs(acc[mi][t][0]), fabs(acc[mi][t][1])));
+      continue;
+    }
     if (oc < col_end) {
 #pragma unroll
       for (int mi = 0; mi < QT; mi++) {
         const int i = mi * 8 + g;
         if (i < q) {
-          if (p.emit_slices) {
+          if (PASS == 2 || p.emit_slices) {
             unsigned long long Y[2][4];   // NT = 4: [e][t];  NT = 2: Y[0] = the lane's 4 columns
 #pragma unroll
             for (int e = 0; e < 2; e++)
@@ -407,6 +437,21 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
     }
   }
 
+  if (PASS == 1) {
+#pragma unroll
+    for (int mi = 0; mi < QT; mi++) {
+      double mx = rowmax[mi];
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const int i = mi * 8 + g;
+      if (t4 == 0 && i < q && mx > 0.0 && isfinite(mx)) {
+        int ex = 0;
+        frexp(mx, &ex);   // mx = m 2^ex, m in [0.5, 1): every entry of the row is below 2^ex
+        atomicMax(p.slice_exp + bb * q + i, ex);
+      }
+    }
+    return;
+  }
   // rank-1 mean term scale and direct kernel terms (once per q-batch)
   if (chunk != 0) return;
   const double* Ub = p.U + bb * q * d;
@@ -461,7 +506,18 @@ static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
   }
   const int64_t warps = p.b * ((p.np + col_chunk - 1) / col_chunk);
   int64_t blocks = (warps + BLK_WARPS - 1) / BLK_WARPS;
-  posterior_blocks_bwd_kernel<QT, RT><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+  static const bool use_bound = (getenv("MCACQ_DA_BOUND") != nullptr) && atoi(getenv("MCACQ_DA_BOUND")) != 0;
+  if (p.emit_slices && !use_bound) {
+    // 0x80808080 = -2139062144: below every frexp exponent
+    if (cudaMemsetAsync(p.slice_exp, 0x80, (size_t)p.b * p.q * sizeof(int32_t), st) != cudaSuccess)
+      return (int)cudaGetLastError();
+    posterior_blocks_bwd_kernel<QT, RT, 1><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+    count_launch();
+    MCACQ_CUDA_CHECK_LAUNCH();
+    posterior_blocks_bwd_kernel<QT, RT, 2><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+  } else {
+    posterior_blocks_bwd_kernel<QT, RT, 0><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+  }
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

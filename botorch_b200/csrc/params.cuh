@@ -39,6 +39,7 @@ struct BlocksBwdParams {
   int emit_slices, G;
   int8_t* slices;             // [G][b*q][np]
   double* slice_scale;        // [b*q]
+  int32_t* slice_exp;         // [b*q]  scratch: exponent of the largest |dA[i][:]| (pass 1 -> pass 2)
   const double* A_absmax;     // [b*q]  max_k |A[i][k]| from the forward pass
   const double* Ab_absmax;    // [r]    max_k |A_base[j][k]|
 };
@@ -62,6 +63,7 @@ struct SRParams {
   double util_param;       // modes 5 / 6: beta' / sqrt(pi / 2)
   const double* Zbar;      // [(r + q)] mean over the samples of every row of Zt (modes 5 / 6)
   int n_con, con_fat;
+  int jitter_f32;        // jitter increments rounded to float32 first (see mcacq_mc.jitter_f32)
   double con_a[4], con_b[4], con_eta[4];
   // backward only
   const double* grad_acq;  // [b]

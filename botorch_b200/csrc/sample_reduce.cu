@@ -311,7 +311,7 @@ sample_reduce_fwd_kernel(SRParams p) {
         // linear_operator psd_safe_cholesky: jitter_new = 1e-8 * (10 ** i), i = attempt - 1
         const double p10[6] = {1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0};
         const double jit_new = 1e-8 * p10[attempt - 1];
-        diag += (jit_new - jit_prev);
+        diag += p.jitter_f32 ? (double)(float)(jit_new - jit_prev) : (jit_new - jit_prev);
         jit_prev = jit_new;
         info = attempt;
       }
@@ -331,6 +331,25 @@ sample_reduce_fwd_kernel(SRParams p) {
       if (ok) break;
     }
     if (!ok) info = 6 | MCACQ_INFO_NOT_PSD;
+    {
+      // conditioning of the q-batch: rho = min_i C_ii^2 / Sxx_ii, the smallest fraction of a point's posterior variance that
+      // is left after conditioning on the baseline draws and on the preceding points of the q-batch (1 = independent points,
+      // -> 0 = the joint covariance is singular); floor(-4 log2 rho), saturated at 255, goes into bits 8..15 of the status
+      // word.  Rounding errors of the posterior blocks reach the value and its gradient amplified by 1 / rho, which is what
+      // the Python layer uses to route ill-conditioned q-batches of the int8 contraction mode to the FP64 contraction.
+      double rho = 1.0;
+      if (lane < q) {
+        const double sii = p.Sxx[bb * q * q + lane * q + lane];
+        const double cii = ok ? Cs[lane * q + lane] : 0.0;
+        rho = (sii > 0.0) ? cii * cii / sii : 0.0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rho = fmin(rho, __shfl_xor_sync(0xffffffffu, rho, o));
+      int cond = 255;
+      if (rho >= 1.0) cond = 0;
+      else if (rho > 0.0) { const double c = -4.0 * log2(rho); cond = c < 255.0 ? (int)c : 255; }
+      info |= cond << MCACQ_INFO_COND_SHIFT;
+    }
     if (lane < q) {
       for (int j = 0; j < q; j++) {
         double v = (j <= lane) ? (ok ? Cs[lane * q + j] : CUDART_NAN) : 0.0;

@@ -136,7 +136,8 @@ class SingleTaskGP(Model):
         # the tensors are kept alive next to the cached strategy (`_strategy_tensors`), so neither their Python identity nor
         # their storage address can be recycled by a replacement tensor while the key is in use
         self._key_tensors = tensors
-        return (self.train_inputs[0].device, settings.contraction.value(), settings.int8_slices.value(), ident)
+        return (self.train_inputs[0].device, settings.contraction.value(), settings.int8_slices.value(),
+                settings.int8_cond_limit.value(), ident)
 
     def _base_kernel(self) -> Kernel:
         k = self.covar_module.base_kernel if isinstance(self.covar_module, ScaleKernel) else self.covar_module

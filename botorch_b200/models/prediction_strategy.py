@@ -119,8 +119,26 @@ class DevicePredictionStrategy:
             Rt_slices=None, Rt_scale=None, R_slices=None, R_scale=None,
         )
         self.int8_probe_error = self.int8_probe_grad_error = None
+        lim = settings.int8_cond_limit.value()
+        self.int8_cond_limit = self.INT8_COND_LIMIT if lim == "auto" else lim
+        self._fp64_view = None
         if contraction == "int8":
             self._select_int8(Xt)
+
+    def fp64_view(self) -> "DevicePredictionStrategy":
+        """The same fitted state with the FP64 DMMA contraction: where the int8 mode sends ill-conditioned q-batches."""
+        if self.contraction != "int8":
+            return self
+        if self._fp64_view is None:
+            import copy
+
+            v = copy.copy(self)
+            v.desc = _lib.Model.from_buffer_copy(self.desc)
+            v.desc.contraction = 0
+            v.contraction = "dmma"
+            v._fp64_view = None
+            self._fp64_view = v
+        return self._fp64_view
 
     # The slices are FIXED-point relative to each row's largest entry, so the int8 contraction reproduces the posterior
     # variance to ~2^-(8G-2) of the PRIOR variance, not of the variance itself: with G = 6 that is ~1e-12 of the prior
@@ -135,6 +153,10 @@ class DevicePredictionStrategy:
     G_BWD_LADDER = (5, 6, 7)
     INT8_PROBE_TOL = 2.5e-10
     INT8_PROBE_GRAD_TOL = 1e-7
+    # q-batches whose conditioning byte floor(-4 log2 rho) exceeds this go through the FP64 contraction (see
+    # acquisition/_fused.py::fused_acquisition): 16 <=> rho < 1/16, i.e. some point of the q-batch keeps less than 6 % of its
+    # posterior variance once the baseline draws and the preceding points are known
+    INT8_COND_LIMIT = 16
 
     def _probe_points(self, Xt: Tensor) -> Tensor:
         """Training points (smallest posterior variances, hence the worst cancellation), the same points displaced by
@@ -192,12 +214,17 @@ class DevicePredictionStrategy:
                 break
         chosen_b = None
         if chosen_f is not None:
+            pairs, pair_gc = self._pair_probe(probe)
+            self.desc.contraction = 0
+            _, gp64 = self._probe_blocks(pairs, pair_gc)
+            gpmax = gp64.abs().max().clamp_min(1e-300)
             for gb in self.G_BWD_LADDER:
                 if not self._int8_exact(gb):
                     break
                 self._set_slices(chosen_f, gb)
                 _, g8 = self._probe_variance_and_grad(probe)
-                gerr = float((g8 - g64).abs().max() / gmax)
+                _, gp8 = self._probe_blocks(pairs, pair_gc)
+                gerr = max(float((g8 - g64).abs().max() / gmax), float((gp8 - gp64).abs().max() / gpmax))
                 if gerr <= self.INT8_PROBE_GRAD_TOL:
                     chosen_b = gb
                     break
@@ -218,19 +245,35 @@ class DevicePredictionStrategy:
         """Posterior variance at P single points and d(sum of variances)/dX through the forward AND backward contraction of
         the current mode (the backward one uses fewer slices, so it is the first to lose digits)."""
         P = probe.shape[0]
+        covar, gX = self._probe_blocks(probe, torch.ones(P, 1, 1, device=self.device, dtype=torch.float64) if backward else None)
+        return covar.reshape(-1), (gX.reshape(P, self.d) if backward else None)
+
+    def _probe_blocks(self, X: Tensor, gcov: Tensor | None) -> tuple[Tensor, Tensor | None]:
+        """Posterior covariance blocks of P q-batches and, with a cotangent `gcov` [P x q x q], d<gcov, covar>/dX."""
+        P, q = X.shape[0], X.shape[1]
         L, st = _lib.lib(), _lib.stream_ptr()
         f64 = dict(device=self.device, dtype=torch.float64)
-        X = probe.contiguous()
-        mean, covar, gX = torch.empty(P, 1, **f64), torch.empty(P, 1, 1, **f64), torch.empty(P, 1, self.d, **f64)
-        ws = self.workspace(P, 1, 0)
-        _lib.check(L.mcacq_posterior(C.byref(self.desc), X.data_ptr(), P, 1, mean.data_ptr(), covar.data_ptr(), ws.data_ptr(),
+        X = X.contiguous()
+        mean, covar, gX = torch.empty(P, q, **f64), torch.empty(P, q, q, **f64), torch.empty(P, q, self.d, **f64)
+        ws = self.workspace(P, q, 0)
+        _lib.check(L.mcacq_posterior(C.byref(self.desc), X.data_ptr(), P, q, mean.data_ptr(), covar.data_ptr(), ws.data_ptr(),
                                      ws.numel(), st), "mcacq_posterior (probe)")
-        if not backward:
-            return covar.reshape(-1), None
-        gm, gc = torch.zeros(P, 1, **f64), torch.ones(P, 1, 1, **f64)
-        _lib.check(L.mcacq_posterior_backward(C.byref(self.desc), X.data_ptr(), P, 1, gm.data_ptr(), gc.data_ptr(),
+        if gcov is None:
+            return covar, None
+        gm, gc = torch.zeros(P, q, **f64), gcov.contiguous()
+        _lib.check(L.mcacq_posterior_backward(C.byref(self.desc), X.data_ptr(), P, q, gm.data_ptr(), gc.data_ptr(),
                                               gX.data_ptr(), ws.data_ptr(), ws.numel(), st), "mcacq_posterior_backward (probe)")
-        return covar.reshape(-1), gX.reshape(P, self.d)
+        return covar, gX
+
+    def _pair_probe(self, probe: Tensor) -> tuple[Tensor, Tensor]:
+        """The cotangent a nearly singular q x q conditional covariance sends backwards: pairs of points 1e-2 of the box apart
+        with gcov = [[1, -1], [-1, 1]], i.e. the gradient of Var(f(x) - f(x')) -- a Schur-complement pivot, whose terms
+        cancel almost completely.  Returns (pairs P x 2 x d, gcov P x 2 x 2)."""
+        n_t = (probe.shape[0] - 256) // 3
+        a, bpt = probe[:n_t, 0], probe[2 * n_t:3 * n_t, 0]        # training points and their 1e-3 displacements
+        pairs = torch.stack([a, a + 10.0 * (bpt - a)], dim=1)
+        gc = torch.tensor([[1.0, -1.0], [-1.0, 1.0]], device=self.device, dtype=torch.float64).expand(pairs.shape[0], 2, 2)
+        return pairs.contiguous(), gc.contiguous()
 
     def _slice_rows(self, Mx: Tensor, G: int) -> tuple[Tensor, Tensor]:
         rows, K = Mx.shape

@@ -9,6 +9,9 @@ is executed:
               1e-7 of the FP64 contraction; a model that no slice count serves runs on "dmma"
               (`DevicePredictionStrategy._select_int8`).  ~2x faster than "dmma".  This is the default.
 `int8_slices` = (g_fwd, g_bwd) pins the slice counts and skips the probe (benchmarks / developer tools only).
+`int8_cond_limit`: q-batches whose conditioning byte floor(-4 log2 rho) (rho = smallest relative Cholesky pivot of the
+              q-batch's conditional covariance) exceeds this limit are re-evaluated through the FP64 contraction; "auto" = the
+              library's calibrated limit (`DevicePredictionStrategy.INT8_COND_LIMIT`), None = never re-route.
 
 `optimizer` selects what `optimize_acqf` uses when no `gen_candidates` is passed:
   * "scipy"  -- `gen_candidates_scipy`: scipy's own L-BFGS-B routine stepped on the host (iterates bit-identical to
@@ -47,4 +50,5 @@ class _Flag:
 
 contraction = _Flag("int8")
 int8_slices = _Flag(None)
+int8_cond_limit = _Flag("auto")
 optimizer = _Flag("scipy")

@@ -57,6 +57,11 @@ extern "C" {
 #define MCACQ_INFO_JITTER_MASK 0x7 /* number of jitter escalations applied (0 = none, 1 -> 1e-8, ... 6 -> 1e-3) */
 #define MCACQ_INFO_NOT_PSD 0x8     /* still not PD after 6 tries  (reference: NotPSDError)   */
 #define MCACQ_INFO_NONFINITE 0x10  /* NaN/Inf in the samples      (reference: NanError)      */
+#define MCACQ_INFO_FLAG_MASK 0x1F  /* the bits above: 0 = nothing to report                    */
+/* bits 8..15: conditioning of the q-batch, floor(-4 log2 rho) saturated at 255, rho = min_i C_ii^2 / Sxx_ii (the smallest
+ * fraction of a point's posterior variance left after conditioning on the baseline draws and the preceding points).   */
+#define MCACQ_INFO_COND_SHIFT 8
+#define MCACQ_INFO_COND_MASK 0xFF00
 
 /* Fitted-model operands (gpytorch DefaultPredictionStrategy caches + BoTorch transforms).   */
 typedef struct {
@@ -127,6 +132,12 @@ typedef struct {
   double con_a[4];
   double con_b[4];
   double con_eta[4];
+  /* psd_safe_cholesky adds `(info > 0) * (jitter_new - jitter_prev)` to the diagonal: a bool tensor times a Python float,
+   * i.e. a tensor of torch's DEFAULT dtype.  With the usual float32 default the increments 1e-8, 9e-8, 9e-7, ... are therefore
+   * rounded to float32 before they reach the fp64 matrix (3e-11 absolute at the 1e-3 level).  1 = reproduce that (the
+   * Python layer passes `torch.get_default_dtype() == torch.float32`), 0 = exact fp64 increments.                      */
+  int32_t jitter_f32;
+  int32_t _pad;
 } mcacq_mc;
 
 const char* mcacq_version(void);
@@ -202,6 +213,15 @@ int mcacq_posterior_backward(const mcacq_model* model, const double* X, int64_t 
 int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc, const double* X,
                       int64_t b, int q, double* acq, int32_t* info, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* The sample / reduce stage of mcacq_acq_forward on caller-provided posterior blocks -- mean [b x q], Sxx [b x q x q],
+ * Sxb [b x q x r] (original outcome scale): replaces `sample_cached_cholesky` (botorch/utils/low_rank.py:84-172; r = 0:
+ * `GPyTorchPosterior.rsample_from_base_samples`, posteriors/gpytorch.py:86-127) followed by `_sample_forward` and the
+ * reductions.  Outputs: acq [b], info [b] (jitter level / NOT_PSD / NONFINITE bits), the factors Bm [b x q x r] and
+ * Cm [b x q x q].  `base` supplies r and L_base only.                                                              */
+int mcacq_sample_reduce_forward(const mcacq_baseline* base, const mcacq_mc* mc, const double* mean, const double* Sxx,
+                                const double* Sxb, int64_t b, int q, double* acq, int32_t* info, double* Bm, double* Cm,
+                                void* stream);
 
 /* grad_X[b x q x d] = d( sum_b grad_acq[b] * acq[b] ) / dX.                                  */
 int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc, const double* X,

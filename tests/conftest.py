@@ -46,8 +46,9 @@ def _restore_settings():
     """Tests flip the package-level flags; every test starts from and returns to the product defaults."""
     from botorch_b200 import settings
 
-    saved = (settings.contraction.value(), settings.int8_slices.value())
+    saved = (settings.contraction.value(), settings.int8_slices.value(), settings.int8_cond_limit.value())
     yield
     settings.contraction.set(saved[0])
     settings.optimizer.set("scipy")
     settings.int8_slices.set(saved[1])
+    settings.int8_cond_limit.set(saved[2])

@@ -72,9 +72,9 @@ def test_edge_shapes_value_and_grad(n, d, q, r, S, b, kernel, contraction):
         v = acqf(Xg)
         assert v.shape == (b,)
         (gr,) = torch.autograd.grad(v.sum(), Xg)
-        # fp64 contraction: 1e-8 / 1e-6.  int8 contraction: its 1e-12 (of the prior variance) absolute accuracy is amplified
-        # by small pivots of the q x q conditional covariances at these tiny n
-        vtol, gtol = (1e-8, 1e-6) if contraction == "dmma" else (1e-7, 1e-5)
+        # one bar for both contraction modes (round 2: the int8 mode picks its slice count per model): 1e-8 / 1e-6 at these
+        # tiny n, where small pivots of the q x q conditional covariances amplify any rounding of the posterior blocks
+        vtol, gtol = 1e-8, 1e-6
         assert float(((v.detach().cpu() - v_o).abs() / v_o.abs().clamp_min(1e-300)).max()) < vtol
         assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max().clamp_min(1e-300)) < gtol
         # empty t-batch: shape-only result, no launch

@@ -83,7 +83,7 @@ def test_random_configuration_matches_oracle(seed):
         Xg = Xq.to(DEV).requires_grad_(True)
         v = acqf(Xg)
         (gr,) = torch.autograd.grad(v.sum(), Xg)
-        vtol, gtol = (1e-8, 1e-6) if c["contraction"] == "dmma" else (1e-7, 2e-5)
+        vtol, gtol = 1e-8, 1e-6   # the same bar in both contraction modes
         assert v.shape == (b,)
         assert float(((v.detach().cpu() - v_o).abs() / v_o.abs().clamp_min(1e-12)).max()) < vtol, c
         assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max().clamp_min(1e-300)) < gtol, c
