@@ -39,8 +39,9 @@ def test_struct_layout_matches_header():
 
     assert ctypes.sizeof(_lib.Model) == 4 * 4 + 4 * 8 + 7 * 8 + 4 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.Baseline) == 8 + 4 * 8
-    # S, fat | tau_relu, tau_max | Zt, best | obj_weight, obj_offset, util_param | Zbar | n_con, con_fat | 3 x double[4]
-    assert ctypes.sizeof(_lib.MC) == 8 + 2 * 8 + 2 * 8 + 3 * 8 + 8 + 8 + 3 * 4 * 8
+    # S, fat | tau_relu, tau_max | Zt, best | obj_weight, obj_offset, util_param | Zbar | n_con, con_fat | 3 x double[4] |
+    # jitter_f32, pad
+    assert ctypes.sizeof(_lib.MC) == 8 + 2 * 8 + 2 * 8 + 3 * 8 + 8 + 8 + 3 * 4 * 8 + 8
 
 
 def test_bad_arguments_return_error_codes(so_path):
