@@ -33,7 +33,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="C1-C3: the qLogEI / qLogNEI hot path (C3 = the headline); C4: MaxPosteriorSampling (Thompson); "
+                         "C5: ModelListGP + qLogEHVI-style objective (bench_extra.py)")
+    ap.add_argument("--trust-regions", type=int, default=8, help="C4: trust regions per GPU per step")
+    ap.add_argument("--candidates", type=int, default=5000, help="C4: candidates per trust region")
+    ap.add_argument("--thompson-samples", type=int, default=4, help="C4: joint posterior samples (batch size) per trust region")
     ap.add_argument("--raw-samples", type=int, default=None, help="override b (total q-batches per step)")
     ap.add_argument("--chunk", type=int, default=8192, help="q-batches per fused call (init_batch_limit analogue)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="q-batches in the CPU baseline sample")
@@ -137,6 +142,13 @@ def cpu_reference(args, data, spec, steps, warmup, sample_b):
 
 def main():
     args = parse()
+    if args.config in ("C4", "C5"):
+        import bench_extra
+
+        if args.impl != "reference" and not torch.cuda.is_available():
+            raise SystemExit("bench.py: CUDA is required (botorch_b200 has no CPU path)")
+        (bench_extra.run_c4 if args.config == "C4" else bench_extra.run_c5)(args, ClockSampler, impl_reference=args.impl == "reference")
+        return
     from botorch_b200.benchmarks import configs
 
     spec = configs.CONFIGS[args.config]

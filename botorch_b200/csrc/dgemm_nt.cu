@@ -18,8 +18,8 @@ constexpr size_t NT_SMEM = (size_t)NT_STAGES * (NT_BM + NT_BN) * NT_LD * sizeof(
 
 __global__ void __launch_bounds__(NT_THREADS, 4)
 dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__ A, int64_t lda,
-                const double* __restrict__ Bt, int64_t ldb, double* __restrict__ C, int64_t ldc,
-                int* __restrict__ tile_counter) {
+                const double* __restrict__ Bt, int64_t ldb, double* C, int64_t ldc,
+                int* __restrict__ tile_counter, double syrk_scale) {
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
   double* sB = smem + NT_STAGES * NT_BM * NT_LD;
@@ -30,7 +30,10 @@ dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__
   const int64_t m_tiles = (M + NT_BM - 1) / NT_BM;
   const int n_tiles = (N + NT_BN - 1) / NT_BN;
   const int k_tiles_total = (K + NT_BK - 1) / NT_BK;
-  const int64_t total = m_tiles * n_tiles;
+  // a_lower == 2: symmetric update C := syrk_scale * (C - A A^T) (Bt == A, M == N, C symmetric on entry): only the tiles on
+  // and below the diagonal are contracted, every result is stored at (row, col) and (col, row)
+  const bool syrk = (a_lower == 2);
+  const int64_t total = syrk ? m_tiles * (m_tiles + 1) / 2 : m_tiles * n_tiles;
 
   for (;;) {
     __syncthreads();
@@ -39,12 +42,18 @@ dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__
     const int64_t tile = s_tile;
     if (tile >= total) break;
     // heaviest row tiles first when A is lower triangular
-    const int64_t mt = a_lower ? (m_tiles - 1 - tile / n_tiles) : tile / n_tiles;
-    const int nt = (int)(tile % n_tiles);
+    int64_t mt = (a_lower == 1) ? (m_tiles - 1 - tile / n_tiles) : tile / n_tiles;
+    int nt = (int)(tile % n_tiles);
+    if (syrk) {   // tile -> (mt, nt <= mt), row-major enumeration of the lower triangle
+      mt = (int64_t)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+      while (mt * (mt + 1) / 2 > tile) mt--;
+      while ((mt + 1) * (mt + 2) / 2 <= tile) mt++;
+      nt = (int)(tile - mt * (mt + 1) / 2);
+    }
     const int64_t row0 = mt * NT_BM;
     const int col0 = nt * NT_BN;
     int kt_end = k_tiles_total;
-    if (a_lower) {
+    if (a_lower == 1) {
       int64_t kmax = row0 + NT_BM;
       if (kmax > K) kmax = K;
       kt_end = (int)((kmax + NT_BK - 1) / NT_BK);
@@ -113,6 +122,17 @@ dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__
         for (int j = 0; j < 4; j++) {
           int gc = col0 + wn * 32 + j * 8 + t4 * 2;
           double* dst = C + gr * ldc + gc;
+          if (syrk) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              if (gc + e < N) {
+                const double v = syrk_scale * (dst[e] - acc[i][j][e]);
+                dst[e] = v;
+                if (nt != mt) C[(int64_t)(gc + e) * ldc + gr] = v;
+              }
+            }
+            continue;
+          }
           if (gc + 1 < N && ((ldc & 1) == 0)) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
           else {
             if (gc < N) dst[0] = acc[i][j][0];
@@ -126,8 +146,23 @@ dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__
 
 }  // namespace mcacq
 
+static int dgemm_nt_launch(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
+                           double* C, int64_t ldc, int32_t* tile_counter, double syrk_scale, void* stream);
+
 extern "C" int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt,
                               int64_t ldb, double* C, int64_t ldc, int32_t* tile_counter, void* stream) {
+  if (a_lower != 0 && a_lower != 1) return MCACQ_EINVAL;
+  return dgemm_nt_launch(a_lower, M, N, K, A, lda, Bt, ldb, C, ldc, tile_counter, 1.0, stream);
+}
+
+extern "C" int mcacq_syrk_sub(int64_t N, int K, const double* A, int64_t lda, double* C, int64_t ldc, double scale,
+                              int32_t* tile_counter, void* stream) {
+  if (N > 0x7fffffff) return MCACQ_EINVAL;
+  return dgemm_nt_launch(2, N, (int)N, K, A, lda, A, lda, C, ldc, tile_counter, scale, stream);
+}
+
+static int dgemm_nt_launch(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
+                           double* C, int64_t ldc, int32_t* tile_counter, double syrk_scale, void* stream) {
   using namespace mcacq;
   if (!A || !Bt || !C || !tile_counter || M < 0 || N < 0 || K <= 0) return MCACQ_EINVAL;
   if (lda < K || ldb < K || ldc < N || (lda & 1) || (ldb & 1) || (K & 1)) return MCACQ_EINVAL;  // 16-byte cp.async chunks
@@ -141,10 +176,12 @@ extern "C" int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double
     cudaError_t e = cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM);
     if (e != cudaSuccess) { sms = 0; return (int)e; }
   }
-  int64_t total = ((M + NT_BM - 1) / NT_BM) * ((N + NT_BN - 1) / NT_BN);
+  if (a_lower == 2 && (M != N || A != Bt)) return MCACQ_EINVAL;
+  const int64_t mtl = (M + NT_BM - 1) / NT_BM;
+  int64_t total = (a_lower == 2) ? mtl * (mtl + 1) / 2 : mtl * ((N + NT_BN - 1) / NT_BN);
   int grid = (int)((total < (int64_t)sms * 4) ? total : (int64_t)sms * 4);
   zero_counter_kernel<<<1, 1, 0, st>>>(tile_counter);
-  dgemm_nt_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(a_lower, M, N, K, A, lda, Bt, ldb, C, ldc, tile_counter);
+  dgemm_nt_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(a_lower, M, N, K, A, lda, Bt, ldb, C, ldc, tile_counter, syrk_scale);
   count_launch(2);
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

@@ -48,8 +48,7 @@ class MaxPosteriorSampling(SamplingStrategy):
 
     def forward(self, X: Tensor, num_samples: int = 1, observation_noise: bool = False) -> Tensor:
         """X: batch_shape x N x d -> batch_shape x num_samples x d rows of X picked by posterior arg-max."""
-        fast = (isinstance(self.model, SingleTaskGP) and self.posterior_transform is None and not observation_noise
-                and X.shape[-2] % 2 == 0)
+        fast = isinstance(self.model, SingleTaskGP) and self.posterior_transform is None and not observation_noise
         if not fast:
             posterior = self.model.posterior(X, observation_noise=observation_noise,
                                              posterior_transform=self.posterior_transform)
@@ -61,10 +60,24 @@ class MaxPosteriorSampling(SamplingStrategy):
         outs = []
         with torch.no_grad():
             for xb in Xf:
-                mean, covar = strat.joint_posterior(xb)
+                if N % 2:
+                    # the DMMA SYRK / TRMM kernels move 16-byte row chunks (even leading dimensions): evaluate the joint
+                    # posterior with one extra point (the centroid) and keep the N x N block of the candidates
+                    mean, covar = strat.joint_posterior(torch.cat([xb, xb.mean(dim=0, keepdim=True)]))
+                    mean, covar = mean[:N], covar[:N, :N].contiguous()
+                else:
+                    mean, covar = strat.joint_posterior(xb)
                 chol = psd_safe_cholesky(covar, max_tries=6)
                 Z = torch.randn(num_samples, N, device=strat.device, dtype=torch.float64)
-                Y = strat.lower_times_samples(chol, Z)  # N x num_samples
+                if N % 2:
+                    # the triangular DMMA kernel moves 16-byte row chunks: pad the factor with one decoupled unit row /
+                    # column and the base samples with a zero column (the extra output row is dropped)
+                    chol = torch.nn.functional.pad(chol, (0, 1, 0, 1))
+                    chol[N, N] = 1.0
+                    Zp = torch.nn.functional.pad(Z, (0, 1))
+                    Y = strat.lower_times_samples(chol, Zp)[:N]
+                else:
+                    Y = strat.lower_times_samples(chol, Z)  # N x num_samples
                 outs.append((Y + mean.unsqueeze(-1)).t())
         samples = torch.stack(outs, dim=1).reshape(num_samples, *batch_shape, N, 1)
         return self.maximize_samples(X, samples, num_samples)

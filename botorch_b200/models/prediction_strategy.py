@@ -347,12 +347,11 @@ class DevicePredictionStrategy:
         Kxx = torch.empty(N, N, **f64)
         _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, U.data_ptr(), N, self.d,
                                      Kxx.data_ptr(), N, st), "cov_cross")
-        G = torch.empty(N, N, **f64)
-        _lib.check(L.mcacq_dgemm_nt(0, N, N, self.np, A.data_ptr(), self.np, A.data_ptr(), self.np, G.data_ptr(), N,
-                                    counter.data_ptr(), st), "dgemm_nt (syrk)")
+        # covar = s^2 (K(X, X) - A A^T) in place: lower tiles only, mirrored stores (csrc/dgemm_nt.cu, mode 2)
+        _lib.check(L.mcacq_syrk_sub(N, self.np, A.data_ptr(), self.np, Kxx.data_ptr(), N, self.y_std**2, counter.data_ptr(), st),
+                   "syrk_sub")
         mean = self.y_mean + self.y_std * (self.mean_const + Kt @ self.alpha)
-        covar = (self.y_std**2) * (Kxx - G)
-        return mean, covar
+        return mean, Kxx
 
     def joint_posterior_with_grad(self, X: Tensor) -> tuple[Tensor, Tensor]:
         """Differentiable `joint_posterior` (N x d -> mean [N], covar [N x N]) for joint posteriors beyond the fused kernels'

@@ -182,6 +182,13 @@ int mcacq_dgemm_tri(int tri_mode, int64_t M, int np, const double* A, const doub
 int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
                    double* C, int64_t ldc, int32_t* tile_counter, void* stream);
 
+/* Symmetric update C[N x N] := scale * (C - A A^T), A [N x K] (K-contiguous, lda and K even), C symmetric on entry: the
+ * `test_test_covar - covar_correction_rhs^T covar_correction_rhs` of gpytorch exact_predictive_covar followed by
+ * Standardize.untransform_posterior's s^2 (scale) for a joint posterior over N points.  Only the tiles on and below the
+ * diagonal are contracted (half the flops of mcacq_dgemm_nt); every entry is stored at (i, j) and (j, i).             */
+int mcacq_syrk_sub(int64_t N, int K, const double* A, int64_t lda, double* C, int64_t ldc, double scale,
+                   int32_t* tile_counter, void* stream);
+
 /* ---- FP64-accurate contraction on the INT8 tensor cores (Ozaki-style splitting; csrc/ozaki_imma.cu) -------------
  * Optional replacement of mcacq_dgemm_tri for `test_train_covar @ covar_cache`:
  *   mcacq_slice_rows    : X[rows x K] (fp64) -> G signed 8-bit slices [G][rows][Kp] (balanced radix-256 digits) + row scale;

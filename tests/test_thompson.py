@@ -83,3 +83,62 @@ def test_max_posterior_sampling_config4_shape():
     # batched X (two trust regions)
     pb = ts_r(Xc.reshape(2, 1000, 20), num_samples=3)
     assert pb.shape == (2, 3, 20)
+
+
+@pytest.mark.gpu
+def test_joint_posterior_at_config4_size_matches_oracle_on_row_slices():
+    """BASELINE config 4 at full size: N = 5000 candidates, n = 2048.  The oracle evaluates 96-row slices of the candidate set
+    (a sub-block of a joint Gaussian's covariance is the joint covariance of the sub-set), incl. the rows with the smallest
+    posterior variance."""
+    from dataclasses import replace
+
+    from botorch_b200.benchmarks import configs
+    from oracle.harness import build_oracle
+
+    dev = torch.device("cuda:0")
+    data = configs.make_problem(replace(configs.C3, n=2048))
+    model = configs.build_model(data, dev)
+    strat = model.prediction_strategy()
+    g = torch.Generator().manual_seed(3)
+    N = 5000
+    center = data.train_X[data.train_Y.argmax()]
+    Xc = (center + 0.4 * (torch.rand(N, 20, generator=g, dtype=torch.float64) - 0.5)).clamp(0.0, 1.0)
+    mean, covar = strat.joint_posterior(Xc.to(dev))
+    assert mean.shape == (N,) and covar.shape == (N, N)
+    gp = build_oracle(data).gp
+    var = covar.diagonal().cpu()
+    slices = [torch.arange(0, 96), torch.arange(N - 96, N), var.argsort()[:96], torch.randperm(N, generator=g)[:96]]
+    for rows in slices:
+        m_o, c_o = gp.posterior_mvn(Xc[rows])
+        blk = covar[rows.to(dev)][:, rows.to(dev)].cpu()
+        assert float((mean[rows.to(dev)].cpu() - m_o).abs().max() / m_o.abs().max()) < 1e-9
+        assert float((blk - c_o).abs().max() / c_o.abs().max()) < 1e-9
+        # and each variance to 1e-9 of itself
+        assert float(((blk.diagonal() - c_o.diagonal()).abs() / c_o.diagonal()).max()) < 1e-9
+
+
+@pytest.mark.gpu
+def test_odd_candidate_count_stays_on_the_cuda_route():
+    """N odd: same kernels (one padding point), same distribution as the even case on the shared candidates."""
+    from dataclasses import replace
+
+    from botorch_b200.benchmarks import configs
+    from botorch_b200.generation import MaxPosteriorSampling
+
+    dev = torch.device("cuda:0")
+    data = configs.make_problem(replace(configs.C3, n=256))
+    model = configs.build_model(data, dev)
+    strat = model.prediction_strategy()
+    torch.manual_seed(0)
+    Xc = torch.rand(301, 20, dtype=torch.float64, device=dev)
+    calls = []
+    orig = strat.lower_times_samples
+    strat.lower_times_samples = lambda chol, Z: (calls.append(chol.shape[-1]), orig(chol, Z))[1]
+    picked = MaxPosteriorSampling(model, replacement=True)(Xc, num_samples=8)
+    assert calls == [302] and picked.shape == (8, 20)     # the DMMA `L z` ran on the padded factor
+    assert all(any(torch.equal(r, x) for x in Xc) for r in picked)
+    # the N x N block that was factorised is the joint covariance of the 301 candidates
+    m_pad, c_pad = strat.joint_posterior(torch.cat([Xc, Xc.mean(dim=0, keepdim=True)]))
+    m_even, c_even = strat.joint_posterior(Xc[:300])
+    assert float((c_pad[:300, :300] - c_even).abs().max() / c_even.abs().max()) < 1e-12
+    assert float((m_pad[:300] - m_even).abs().max()) < 1e-12
