@@ -11,7 +11,9 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0")
 import os
 from botorch_b200 import settings
-settings.contraction.set(os.environ.get("MCACQ_CONTRACTION", "dmma"))
+settings.contraction.set(os.environ.get("MCACQ_CONTRACTION", "int8"))
+if os.environ.get("MCACQ_SLICES"):
+    settings.int8_slices.set(tuple(int(v) for v in os.environ["MCACQ_SLICES"].split(",")))
 data = configs.make_problem(configs.CONFIGS[cfg])
 model = configs.build_model(data, dev)
 acqf = configs.build_acqf(data, model)
