@@ -121,9 +121,15 @@ __device__ __forceinline__ double log_feas_term(double u, int fat, double& dlf) 
 
 // Per-sample, per-point utility of a posterior sample value y: objective (affine), utility mode, constraint weighting.
 // dy = d val / d y,  dm = d val / d mu_i (modes 5 / 6: mu_i = MC mean of the objective).
-template <bool GRAD>
+// PLAIN: the default qLogEI / qLogNEI configuration (utility mode 1, identity objective, no constraints) with the mode
+// fields folded to constants, so that the other modes cost neither registers nor issue slots on the benchmark path.
+template <bool GRAD, bool PLAIN>
 __device__ __forceinline__ double sr_element(const SRParams& p, double yi, double bst, double mu, double inv_tau_relu,
                                              double& dy, double& dm) {
+  if (PLAIN) {
+    dm = 0.0;
+    return log_improve<GRAD>(yi - bst, p.tau_relu, inv_tau_relu, 1, dy);
+  }
   const double obj = fma(p.obj_w, yi, p.obj_o);
   double val, dobj = 0.0;
   dm = 0.0;
@@ -239,10 +245,11 @@ __device__ __forceinline__ int coef_pitch(int q) { return (q + 1) & ~1; }
 // W > 1 ("wide", for the few q-batches of an optimiser round): W x 128 threads evaluate the per-sample utilities, park them
 // in shared memory, and the first 128 threads then fold them in exactly the order of the W = 1 kernel -- results are
 // bit-identical for every W, only the latency per q-batch changes.
-template <int QMAX, int NS, int W>
+template <int QMAX, int NS, int W, bool PLAIN>
 __global__ void __launch_bounds__(SR_THREADS * W)
 sample_reduce_fwd_kernel(SRParams p) {
   constexpr int NT = SR_THREADS * W, NW = SR_WARPS * W;
+  const int fat = PLAIN ? 1 : p.fat;
   extern __shared__ __align__(16) double sm[];
   const int q = p.q, r = p.r, S = p.S;
   const int QP = coef_pitch(q);
@@ -362,7 +369,7 @@ sample_reduce_fwd_kernel(SRParams p) {
   __syncthreads();
 
   // MC mean of the objective per point in closed form: obj_w (mean_i + sum_j coef_ij Zbar_j) + obj_o
-  if (p.fat >= 5) {
+  if (fat >= 5) {
     for (int i = tid; i < q; i += NT) {
       double m = smean[i];
       for (int j = 0; j < r + q; j++) m = fma(coefT[j * QP + i], p.Zbar[j], m);
@@ -401,17 +408,17 @@ sample_reduce_fwd_kernel(SRParams p) {
           const double yi = y[i] + smean[i];
           if (!isfinite(yi)) nonfinite = true;
           double dl, dmm;
-          li[i] = sr_element<false>(p, yi, bst, (p.fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
+          li[i] = sr_element<false, PLAIN>(p, yi, bst, (fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
         } else li[i] = -CUDART_INF;
       }
-      fmv[s0] = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
+      fmv[s0] = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, fat, wdummy);
     }
     if (nonfinite) s_nonfinite = 1;
     __syncthreads();
     if (tid < SR_THREADS) {
       for (int s0 = tid; s0 < S; s0 += SR_THREADS) {   // the W = 1 kernel's per-thread sample order
         const double fm = fmv[s0];
-        if (p.fat >= 2) ls += fm;
+        if (fat >= 2) ls += fm;
         else if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
         else lse_push(lm, ls, fm);
       }
@@ -452,11 +459,11 @@ sample_reduce_fwd_kernel(SRParams p) {
               const double yi = y[ns][i] + smean[i];
               if (!isfinite(yi)) nonfinite = true;
               double dl, dmm;
-              li[i] = sr_element<false>(p, yi, bst, (p.fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
+              li[i] = sr_element<false, PLAIN>(p, yi, bst, (fat >= 5) ? smu[i] : 0.0, inv_tau_relu, dl, dmm);
             } else li[i] = -CUDART_INF;
           }
-          const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, p.fat, wdummy);
-          if (p.fat >= 2) ls += fm;  // plain mean over the samples
+          const double fm = q_reduce<QMAX, false>(li, q, p.tau_max, inv_tau_max, fat, wdummy);
+          if (fat >= 2) ls += fm;  // plain mean over the samples
           else if (fm == CUDART_INF) { lm = fm; ls = 1.0; }
           else lse_push(lm, ls, fm);
         }
@@ -470,7 +477,7 @@ sample_reduce_fwd_kernel(SRParams p) {
     for (int o = 16; o > 0; o >>= 1) {
       const double m2 = __shfl_xor_sync(0xffffffffu, lm, o);
       const double s2 = __shfl_xor_sync(0xffffffffu, ls, o);
-      if (p.fat >= 2) ls += s2;
+      if (fat >= 2) ls += s2;
       else lse_merge(lm, ls, m2, s2);
     }
     if (lane == 0) { red[2 * warp] = lm; red[2 * warp + 1] = ls; }
@@ -479,11 +486,11 @@ sample_reduce_fwd_kernel(SRParams p) {
   if (tid == 0) {
     double m = red[0], s = red[1];
     for (int w = 1; w < SR_WARPS; w++) {
-      if (p.fat >= 2) s += red[2 * w + 1];
+      if (fat >= 2) s += red[2 * w + 1];
       else lse_merge(m, s, red[2 * w], red[2 * w + 1]);
     }
     double res;
-    if (p.fat >= 2) res = s / (double)S;
+    if (fat >= 2) res = s / (double)S;
     else if (S == 0 || m == -CUDART_INF) res = -CUDART_INF;
     else if (isinf(m)) res = m;
     else res = m + log(s) - log((double)S);
@@ -496,10 +503,11 @@ sample_reduce_fwd_kernel(SRParams p) {
 // Backward ------------------------------------------------------------------------------------------
 // W > 1: the per-sample weights (pass A, the expensive part) are evaluated by W x 128 threads; the contraction with the
 // base samples (pass B) keeps the 4-warp split of the W = 1 kernel, so the results are bit-identical for every W.
-template <int QMAX, int NS, int W>
+template <int QMAX, int NS, int W, bool PLAIN>
 __global__ void __launch_bounds__(SR_THREADS * W)
 sample_reduce_bwd_kernel(SRParams p, int chunk) {
   constexpr int NT = SR_THREADS * W, NW = SR_WARPS * W;
+  const int fat = PLAIN ? 1 : p.fat;
   extern __shared__ __align__(16) double sm[];
   const int q = p.q, r = p.r, S = p.S;
   const int QP = coef_pitch(q);
@@ -534,7 +542,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   const double gout = p.grad_acq[bb];
   const double lse_total = p.acq[bb] + log((double)S);
   const double inv_tau_relu = 1.0 / p.tau_relu, inv_tau_max = 1.0 / p.tau_max;
-  const bool mc_mean = p.fat >= 5;
+  const bool mc_mean = fat >= 5;
   if (mc_mean) {
     for (int i = tid; i < q; i += NT) {
       double m = smean[i];
@@ -581,12 +589,12 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           double li[QMAX], dli[QMAX], dmu[QMAX], w[QMAX];
 #pragma unroll
           for (int i = 0; i < QMAX; i++) {
-            if (i < q) li[i] = sr_element<true>(p, y[ns][i] + smean[i], bst, mc_mean ? smu[i] : 0.0, inv_tau_relu, dli[i], dmu[i]);
+            if (i < q) li[i] = sr_element<true, PLAIN>(p, y[ns][i] + smean[i], bst, mc_mean ? smu[i] : 0.0, inv_tau_relu, dli[i], dmu[i]);
             else { li[i] = -CUDART_INF; dli[i] = 0.0; dmu[i] = 0.0; }
           }
-          const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, inv_tau_max, p.fat, w);
+          const double fm = q_reduce<QMAX, true>(li, q, p.tau_max, inv_tau_max, fat, w);
           double ws;
-          if (p.fat >= 2) ws = gout / (double)S;
+          if (fat >= 2) ws = gout / (double)S;
           else if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
           else ws = gout * exp(fm - lse_total);
           double* gys = gy + (size_t)(s0 + ns - c0) * GP;
@@ -785,11 +793,15 @@ static size_t bwd_smem(int q, int r, int chunk, int qmax, bool mc_mean) {
           (size_t)SR_WARPS * qmax * 8 + 2 * (size_t)q + (mc_mean ? (size_t)(chunk + 4) * GP : 0)) * sizeof(double);
 }
 
-template <int QMAX, int NS, int W>
+static inline bool sr_plain(const SRParams& p) {
+  return p.fat == 1 && p.n_con == 0 && p.obj_w == 1.0 && p.obj_o == 0.0;
+}
+
+template <int QMAX, int NS, int W, bool PLAIN = false>
 static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
   size_t smem = fwd_smem(p.q, p.r, p.S, W > 1);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
-  auto kern = sample_reduce_fwd_kernel<QMAX, NS, W>;
+  auto kern = sample_reduce_fwd_kernel<QMAX, NS, W, PLAIN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)p.b, SR_THREADS * W, smem, st>>>(p);
   count_launch();
@@ -797,7 +809,7 @@ static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
   return 0;
 }
 
-template <int QMAX, int NS, int W>
+template <int QMAX, int NS, int W, bool PLAIN = false>
 static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
   const bool mc_mean = p.fat >= 5;
@@ -808,7 +820,7 @@ static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   if ((int64_t)chunk * (p.q | 1) < (int64_t)p.q * p.r) chunk = (p.q * p.r + (p.q | 1) - 1) / (p.q | 1);
   size_t smem = bwd_smem(p.q, p.r, chunk, QMAX, mc_mean);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
-  auto kern = sample_reduce_bwd_kernel<QMAX, NS, W>;
+  auto kern = sample_reduce_bwd_kernel<QMAX, NS, W, PLAIN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)p.b, SR_THREADS * W, smem, st>>>(p, chunk);
   count_launch();
@@ -822,6 +834,7 @@ int sample_reduce_fwd(const SRParams& p, cudaStream_t st) {
   // one sample per thread and pass: more resident warps beat per-thread ILP here (the transcendental chains do not
   // interleave across samples): 1.55 -> 0.96 ms forward, 2.86 -> 1.83 ms backward per C3 chunk
   const bool wide = sr_use_wide(p.b);
+  if (p.q <= 8 && sr_plain(p)) return wide ? launch_sr_fwd<8, 1, 4, true>(p, st) : launch_sr_fwd<8, 1, 1, true>(p, st);
   if (p.q <= 8) return wide ? launch_sr_fwd<8, 1, 4>(p, st) : launch_sr_fwd<8, 1, 1>(p, st);
   if (p.q <= 16) return wide ? launch_sr_fwd<16, 1, 4>(p, st) : launch_sr_fwd<16, 1, 1>(p, st);
   return launch_sr_fwd<32, 1, 1>(p, st);
@@ -831,6 +844,7 @@ int sample_reduce_bwd(const SRParams& p, cudaStream_t st) {
   if (p.q <= 0 || p.q > MCACQ_MAX_Q || p.r < 0 || p.S <= 0) return MCACQ_ELIMIT;
   if (p.b == 0) return 0;
   const bool wide = sr_use_wide(p.b);
+  if (p.q <= 8 && sr_plain(p)) return wide ? launch_sr_bwd<8, 1, 4, true>(p, st) : launch_sr_bwd<8, 1, 1, true>(p, st);
   if (p.q <= 8) return wide ? launch_sr_bwd<8, 1, 4>(p, st) : launch_sr_bwd<8, 1, 1>(p, st);
   if (p.q <= 16) return launch_sr_bwd<16, 1, 1>(p, st);
   return launch_sr_bwd<32, 1, 1>(p, st);
