@@ -302,7 +302,16 @@ def main():
                         _, oval = optimize_acqf(acqf, **okw)
                         torch.cuda.synchronize()
                         opt = {"wall_ms": (_time.perf_counter() - t0) * 1e3, "q": spec.q, "num_restarts": spec.num_restarts,
-                               "raw_samples": spec.raw_samples, "maxiter": 50, "acq_value": float(oval)}
+                               "raw_samples": spec.raw_samples, "maxiter": 50, "acq_value": float(oval),
+                               "optimizer": "scipy (default): scipy's setulb stepped on the host, one fused fwd+bwd per round"}
+                        # the same call with the device-resident L-BFGS-B (settings.optimizer('device'): CUDA-graph rounds)
+                        with settings.optimizer("device"):
+                            optimize_acqf(acqf, **okw)
+                            torch.cuda.synchronize()
+                            t0 = _time.perf_counter()
+                            _, oval_d = optimize_acqf(acqf, **okw)
+                            torch.cuda.synchronize()
+                            opt["device_optimizer"] = {"wall_ms": (_time.perf_counter() - t0) * 1e3, "acq_value": float(oval_d)}
                 phases = {"optimize_acqf": opt,
                           "sweep_forward_only_points_per_s": pts_local_scale * args.steps / (ms_fwd * 1e-3),
                           "sweep_forward_only_ms_per_step": ms_fwd / args.steps,
