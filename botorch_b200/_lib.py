@@ -21,6 +21,7 @@ KERNEL_MATERN52 = 1
 TRI_UPPER, TRI_LOWER, TRI_DENSE = 0, 1, 2
 INFO_JITTER_MASK, INFO_NOT_PSD, INFO_NONFINITE = 0x7, 0x8, 0x10
 INFO_FLAG_MASK, INFO_COND_SHIFT, INFO_COND_MASK = 0x1F, 8, 0xFF00
+INFO_VAR_SHIFT, INFO_VAR_MASK = 16, 0xFF0000
 MAX_Q, MAX_D, MAX_R = 32, 64, 64
 
 _ERRORS = {-1: "MCACQ_EINVAL (bad argument)", -2: "MCACQ_ELIMIT (q/r/d/S outside compiled limits)",
@@ -73,7 +74,7 @@ EXPORTS = [
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
-    "mcacq_sample_reduce_forward", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
+    "mcacq_sample_reduce_forward", "mcacq_info_summary", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
 ]
 
 
@@ -107,6 +108,7 @@ def lib() -> C.CDLL:
     L.mcacq_workspace_bytes_model.argtypes = [C.POINTER(Model), i64, i32, i32]
     L.mcacq_workspace_bytes_model.restype = sz
     L.mcacq_sample_reduce_forward.argtypes = [C.POINTER(Baseline), C.POINTER(MC), vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    L.mcacq_info_summary.argtypes = [vp, i64, vp, vp]
     L.mcacq_lbfgsb_state_bytes.argtypes = [i64, i32]
     L.mcacq_lbfgsb_state_bytes.restype = sz
     L.mcacq_lbfgsb_init.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp]

@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import torch
 from torch import Tensor
 
-from .. import _lib
+from .. import _lib, settings
 from ..exceptions.errors import NanError, NotPSDError
 from ..exceptions.warnings import NumericalWarning
 from ..models.prediction_strategy import DevicePredictionStrategy
@@ -82,13 +82,15 @@ class LaunchStats:
         cls.launches += int(_lib.lib().mcacq_last_launch_count())
 
 
-def _info_summary(info: Tensor) -> tuple[int, int]:
-    """(OR-free summary of the status words, one device synchronisation): largest flag part and largest conditioning byte."""
+def _info_summary(info: Tensor) -> tuple[int, int, int]:
+    """(OR of the flag bits, largest conditioning byte, largest variance-collapse byte) of the status words: one small launch
+    (`mcacq_info_summary`) and one 12-byte read -- the only device synchronisation of a fused forward call."""
     if not info.numel():
-        return 0, 0
-    # flag bits: all non-negative bit sets, max == 0 <=> all clear; conditioning byte: bits 8..15 (monotone in the word)
-    flags, top = torch.stack([(info & _lib.INFO_FLAG_MASK).max(), info.max()]).tolist()
-    return int(flags), (int(top) & _lib.INFO_COND_MASK) >> _lib.INFO_COND_SHIFT
+        return 0, 0, 0
+    out = torch.empty(3, dtype=torch.int32, device=info.device)
+    _lib.check(_lib.lib().mcacq_info_summary(info.data_ptr(), info.numel(), out.data_ptr(), _lib.stream_ptr()), "mcacq_info_summary")
+    flags, cond, vbyte = out.tolist()
+    return int(flags), int(cond), int(vbyte)
 
 
 def _raise_on_info(info: Tensor, flags: int | None = None) -> None:
@@ -185,15 +187,26 @@ def fused_acquisition(X: Tensor, strat: DevicePredictionStrategy, base: Baseline
     int8 contraction mode: the fixed-point contraction reproduces the posterior blocks to an ABSOLUTE accuracy (a fraction of
     the prior variance, which `DevicePredictionStrategy._select_int8` bounds per fitted model), and a q-batch whose joint
     covariance is nearly singular amplifies any absolute perturbation by 1 / rho (rho = smallest relative Cholesky pivot,
-    reported per q-batch in the status word).  q-batches beyond `strat.int8_cond_limit` are therefore re-evaluated -- value
-    and gradient -- through the FP64 DMMA contraction, so that the mode's accuracy does not depend on where X lies."""
-    limit = strat.int8_cond_limit if strat.contraction == "int8" else None
+    reported per q-batch in the status word), and a point whose variance has collapsed to a small fraction of the prior has
+    lost that many digits of `prior - |a|^2`.  q-batches beyond `strat.int8_cond_limit` or `strat.int8_var_byte_limit` are
+    therefore re-evaluated -- value and gradient -- through the FP64 DMMA contraction, so that the mode's accuracy does not
+    depend on where X lies."""
+    int8 = strat.contraction == "int8"
+    if int8 and settings.int8_max_slices.value():
+        strat = strat.max_slices_view()
+    limit = strat.int8_cond_limit if int8 else None
+    vlimit = strat.int8_var_byte_limit if int8 else None
     holder = {}
-    X8 = _DropRows.apply(X, holder) if (limit is not None and X.requires_grad and torch.is_grad_enabled()) else X
+    X8 = _DropRows.apply(X, holder) if (int8 and X.requires_grad and torch.is_grad_enabled()) else X
     acq, info = FusedMCAcquisition.apply(X8, strat, base, mc)
-    flags, cond = _info_summary(info)
-    if limit is not None and cond > limit:
-        idx = ((info >> _lib.INFO_COND_SHIFT) & 0xFF).gt(limit).nonzero().squeeze(-1)
+    flags, cond, vbyte = _info_summary(info)
+    if (limit is not None and cond > limit) or (vlimit is not None and vbyte > vlimit):
+        bad = torch.zeros_like(info, dtype=torch.bool)
+        if limit is not None:
+            bad |= ((info >> _lib.INFO_COND_SHIFT) & 0xFF).gt(limit)
+        if vlimit is not None:
+            bad |= ((info >> _lib.INFO_VAR_SHIFT) & 0xFF).gt(vlimit)
+        idx = bad.nonzero().squeeze(-1)
         holder["idx"] = idx
         acq64, info64 = FusedMCAcquisition.apply(X.index_select(0, idx), strat.fp64_view(), base, mc)
         acq = acq.index_copy(0, idx, acq64)       # the int8 results of these q-batches (and their gradient path) are dropped

@@ -34,6 +34,7 @@ int posterior_blocks_fwd(const BlocksParams& p, cudaStream_t st);
 int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st);
 int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
+int info_summary(const int32_t* info, int64_t b, int32_t* out, cudaStream_t st);
 
 struct Workspace {
   double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale, *mean_part,
@@ -251,7 +252,7 @@ static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc
   sp.b = b; sp.q = q; sp.r = r; sp.S = mc->S; sp.fat = mc->fat;
   sp.tau_relu = mc->tau_relu; sp.tau_max = mc->tau_max;
   sp.obj_w = mc->obj_weight; sp.obj_o = mc->obj_offset; sp.util_param = mc->util_param; sp.Zbar = mc->Zbar;
-  sp.n_con = mc->n_con; sp.con_fat = mc->con_fat; sp.jitter_f32 = mc->jitter_f32;
+  sp.n_con = mc->n_con; sp.con_fat = mc->con_fat; sp.jitter_f32 = mc->jitter_f32; sp.prior_var = 0.0;
   for (int k = 0; k < 4; k++) { sp.con_a[k] = mc->con_a[k]; sp.con_b[k] = mc->con_b[k]; sp.con_eta[k] = mc->con_eta[k]; }
   sp.mean = w.mean; sp.Sxx = w.Sxx; sp.Sxb = w.Sxb;
   sp.L_base = r > 0 ? base->L_base : nullptr;
@@ -284,7 +285,13 @@ extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline*
   SRParams sp;
   fill_sr(sp, base, mc, b, q, w);
   sp.acq = acq; sp.info = info;
+  sp.prior_var = model->outputscale * model->y_std * model->y_std;
   return sample_reduce_fwd(sp, st);
+}
+
+extern "C" int mcacq_info_summary(const int32_t* info, int64_t b, int32_t* out3, void* stream) {
+  if (!info || !out3 || b < 0) return MCACQ_EINVAL;
+  return info_summary(info, b, out3, (cudaStream_t)stream);
 }
 
 extern "C" int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc,

@@ -63,6 +63,7 @@ struct SRParams {
   double util_param;       // modes 5 / 6: beta' / sqrt(pi / 2)
   const double* Zbar;      // [(r + q)] mean over the samples of every row of Zt (modes 5 / 6)
   int n_con, con_fat;
+  double prior_var;      // outputscale * y_std^2 (0: no variance-collapse byte in the status word)
   int jitter_f32;        // jitter increments rounded to float32 first (see mcacq_mc.jitter_f32)
   double con_a[4], con_b[4], con_eta[4];
   // backward only

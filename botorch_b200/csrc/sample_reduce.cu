@@ -356,6 +356,23 @@ sample_reduce_fwd_kernel(SRParams p) {
       if (rho >= 1.0) cond = 0;
       else if (rho > 0.0) { const double c = -4.0 * log2(rho); cond = c < 255.0 ? (int)c : 255; }
       info |= cond << MCACQ_INFO_COND_SHIFT;
+      // variance collapse of the q-batch: floor(-4 log2 min_i Sxx_ii / prior), saturated at 255, in bits 16..23.  Sxx = prior
+      // - |a|^2 is a difference: a contraction that is accurate to a FRACTION OF THE PRIOR (the int8 mode) reproduces Sxx_ii
+      // to that fraction divided by Sxx_ii / prior, which is what the Python layer bounds per fitted model.
+      int vbyte = 0;
+      if (p.prior_var > 0.0) {
+        double vr = 1.0;
+        if (lane < q) {
+          const double sii = p.Sxx[bb * q * q + lane * q + lane];
+          vr = (sii > 0.0) ? sii / p.prior_var : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vr = fmin(vr, __shfl_xor_sync(0xffffffffu, vr, o));
+        vbyte = 255;
+        if (vr >= 1.0) vbyte = 0;
+        else if (vr > 0.0) { const double c = -4.0 * log2(vr); vbyte = c < 255.0 ? (int)c : 255; }
+      }
+      info |= vbyte << MCACQ_INFO_VAR_SHIFT;
     }
     if (lane < q) {
       for (int j = 0; j < q; j++) {
@@ -823,6 +840,38 @@ static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   auto kern = sample_reduce_bwd_kernel<QMAX, NS, W, PLAIN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)p.b, SR_THREADS * W, smem, st>>>(p, chunk);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// out[0] = OR of the flag bits, out[1] = largest conditioning byte, out[2] = largest variance-collapse byte of info[0..b)
+__global__ void info_summary_kernel(const int32_t* __restrict__ info, int64_t b, int32_t* __restrict__ out) {
+  int fl = 0, c = 0, v = 0;
+  for (int64_t i = threadIdx.x; i < b; i += blockDim.x) {
+    const int w = info[i];
+    fl |= w & MCACQ_INFO_FLAG_MASK;
+    c = max(c, (w & MCACQ_INFO_COND_MASK) >> MCACQ_INFO_COND_SHIFT);
+    v = max(v, (w & MCACQ_INFO_VAR_MASK) >> MCACQ_INFO_VAR_SHIFT);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+    c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
+  __shared__ int sf[32], sc[32], sv[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sf[warp] = fl; sc[warp] = c; sv[warp] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { fl |= sf[w]; c = max(c, sc[w]); v = max(v, sv[w]); }
+    out[0] = fl; out[1] = c; out[2] = v;
+  }
+}
+
+int info_summary(const int32_t* info, int64_t b, int32_t* out, cudaStream_t st) {
+  info_summary_kernel<<<1, 1024, 0, st>>>(info, b, out);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

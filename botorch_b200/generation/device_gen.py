@@ -94,7 +94,9 @@ class _FusedRound:
 
         self.opt, self.q, self.d = opt, q, d
         N = opt.N
-        self.strat = acqf.model.prediction_strategy()
+        # no host between the launches of a captured round, hence no re-routing of ill-conditioned / collapsed q-batches: the
+        # rounds use the int8 mode's most accurate slice counts instead (FP64-level; a round is a few hundred rows)
+        self.strat = acqf.model.prediction_strategy().max_slices_view()
         self.base = acqf._baseline_operands() if hasattr(acqf, "_baseline_operands") else None
         Xv = opt.X.view(N, q, d)
         self.mc = acqf._mc_operands(Xv)

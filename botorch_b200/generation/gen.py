@@ -12,6 +12,8 @@ import numpy as np
 import torch
 from torch import Tensor
 
+from .. import settings
+
 from ..exceptions.errors import OptimizationGradientError, UnsupportedError
 from ..exceptions.warnings import OptimizationWarning
 from ..optim.batched_lbfgs_b import fmin_l_bfgs_b_batched
@@ -50,7 +52,10 @@ def gen_candidates_scipy(initial_conditions: Tensor, acquisition_function, lower
     clamped = columnwise_clamp(X=initial_conditions, lower=lower_bounds, upper=upper_bounds, raise_on_violation=True)
 
     def f(x):
-        return -acquisition_function(x)
+        # optimiser rounds are a few hundred rows: the int8 mode runs them with its most accurate slice counts (FP64-level,
+        # no variance-collapse re-routing; the choice depends on the PHASE, not on how a batch is chunked)
+        with settings.int8_max_slices(True):
+            return -acquisition_function(x)
 
     nb, q, d = clamped.shape
     x0 = _arrayify(clamped).reshape(nb, -1)

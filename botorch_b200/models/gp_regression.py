@@ -226,10 +226,27 @@ class SingleTaskGP(Model):
         b, q, _ = Xf.shape
         step = max(1, max_rows // q)
         if b <= step:
-            return _PosteriorBlocks.apply(Xf, strat)
+            return self._posterior_blocks_checked(Xf, strat)
         means, covars = [], []
         for i in range(0, b, step):
-            m, c = _PosteriorBlocks.apply(Xf[i:i + step], strat)
+            m, c = self._posterior_blocks_checked(Xf[i:i + step], strat)
             means.append(m)
             covars.append(c)
         return torch.cat(means), torch.cat(covars)
+
+    @staticmethod
+    def _posterior_blocks_checked(Xf: Tensor, strat: DevicePredictionStrategy):
+        """`_PosteriorBlocks` plus the int8 mode's variance-collapse rule (DevicePredictionStrategy._select_int8): q-batches with
+        a point whose variance has dropped below `int8_var_ratio_limit` of the prior are re-evaluated through the FP64
+        contraction, so `posterior.variance` keeps its relative accuracy at (and next to) training points."""
+        mean, covar = _PosteriorBlocks.apply(Xf, strat)
+        lim = strat.int8_var_ratio_limit if strat.contraction == "int8" else None
+        if lim is None or Xf.shape[0] == 0:
+            return mean, covar
+        prior = strat.y_std * strat.y_std * strat.outputscale
+        low = covar.detach().diagonal(dim1=-1, dim2=-2).amin(dim=-1) < lim * prior
+        if bool(low.any()):
+            idx = low.nonzero().squeeze(-1)
+            m64, c64 = _PosteriorBlocks.apply(Xf.index_select(0, idx), strat.fp64_view())
+            mean, covar = mean.index_copy(0, idx, m64), covar.index_copy(0, idx, c64)
+        return mean, covar

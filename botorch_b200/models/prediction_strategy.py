@@ -10,6 +10,7 @@ triangular solve (a plain library call on an n x n matrix, off the per-evaluatio
 from __future__ import annotations
 
 import ctypes as C
+import os
 import warnings
 
 import torch
@@ -122,8 +123,36 @@ class DevicePredictionStrategy:
         lim = settings.int8_cond_limit.value()
         self.int8_cond_limit = self.INT8_COND_LIMIT if lim == "auto" else lim
         self._fp64_view = None
+        self._max_view = None
+        self.int8_var_ratio_limit, self.int8_var_byte_limit = None, None
         if contraction == "int8":
             self._select_int8(Xt)
+            if lim is None:   # settings.int8_cond_limit(None) switches every run-time re-routing off (developer tools)
+                self.int8_var_ratio_limit, self.int8_var_byte_limit = None, None
+
+    def max_slices_view(self) -> "DevicePredictionStrategy":
+        """The same fitted state with the largest exact slice counts (7 / 7 when n allows): 2^-54 of the prior, i.e. FP64-level
+        accuracy without the run-time re-routing.  For callers that cannot look at the status words between launches (the
+        CUDA-graph rounds of the device-resident optimiser); those calls are a few hundred rows, where slices cost nothing."""
+        if self.contraction != "int8":
+            return self
+        if getattr(self, "_max_view", None) is None:
+            import copy
+
+            G = max(g for g in self.G_BWD_LADDER if self._int8_exact(g))
+            v = copy.copy(self)
+            v.desc = _lib.Model.from_buffer_copy(self.desc)
+            v._fp64_view = None
+            v._max_view = v
+            v.Rt_slices, v.Rt_scale = (self.Rt_slices, self.Rt_scale) if self.g_fwd == G else self._slice_rows(self.Rt, G)
+            v.R_slices, v.R_scale = (self.R_slices, self.R_scale) if self.g_bwd == G else self._slice_rows(self.R, G)
+            v.g_fwd = v.g_bwd = G
+            v.desc.g_fwd = v.desc.g_bwd = G
+            v.desc.Rt_slices, v.desc.Rt_scale = v.Rt_slices.data_ptr(), v.Rt_scale.data_ptr()
+            v.desc.R_slices, v.desc.R_scale = v.R_slices.data_ptr(), v.R_scale.data_ptr()
+            v.int8_var_ratio_limit, v.int8_var_byte_limit = None, None
+            self._max_view = v
+        return self._max_view
 
     def fp64_view(self) -> "DevicePredictionStrategy":
         """The same fitted state with the FP64 DMMA contraction: where the int8 mode sends ill-conditioned q-batches."""
@@ -142,13 +171,16 @@ class DevicePredictionStrategy:
 
     # The slices are FIXED-point relative to each row's largest entry, so the int8 contraction reproduces the posterior
     # variance to ~2^-(8G-2) of the PRIOR variance, not of the variance itself: with G = 6 that is ~1e-12 of the prior
-    # (5e-11 of the variance over the search box, 1.2e-8 exactly AT the C3 training points, where it has collapsed by four
-    # orders of magnitude); every extra slice buys 2^-8.  `_select_int8` therefore measures, per fitted model, the
-    # variance and gradient error of the int8 path against the FP64 contraction on a probe set built around the training
-    # points (the worst cancellation) and picks the SMALLEST number of slices that keeps the variance within 2.5e-10
-    # pointwise (4x inside the north-star bar of 1e-9) and the variance gradient within 1e-7 of its largest component on
-    # that worst-case probe set (the acquisition gradients of the parity tests then sit at 1e-8 or below); a model no
-    # ladder entry serves runs on 'dmma'.
+    # (5e-11 of the variance over the search box, 2e-9 ... 1.2e-8 exactly AT the C1-C3 training points, where it has collapsed
+    # by four orders of magnitude); every extra slice buys 2^-8.  `_select_int8` therefore measures, per fitted model, the
+    # ABSOLUTE accuracy delta_G of the int8 variances (as a fraction of the prior) against the FP64 contraction on a probe set
+    # built around the training points (the worst cancellation) plus uniform box points, and derives the variance-collapse
+    # limit `ratio_limit = delta_G / INT8_PROBE_TOL`: a point whose variance is at least that fraction of the prior is within
+    # 2.5e-10 relatively (4x inside the north-star bar of 1e-9); points below it are recognised at run time (status-word byte
+    # of `sample_reduce`, or the returned variances of `model.posterior`) and re-evaluated through the FP64 contraction.  The
+    # SMALLEST forward slice count whose limit leaves all uniform box probes on the int8 path is used (C1-C3: 6 -- ordinary
+    # points keep > 2 % of the prior variance, the limit is ~1 %), then the smallest backward count that keeps the variance
+    # gradients (singles and near pairs) within 1e-7 of their largest component; a model no ladder entry serves runs on 'dmma'.
     G_FWD_LADDER = (6, 7)
     G_BWD_LADDER = (5, 6, 7)
     INT8_PROBE_TOL = 2.5e-10
@@ -189,17 +221,21 @@ class DevicePredictionStrategy:
         return self.np * 16384 * g < 2**31
 
     def _select_int8(self, Xt: Tensor) -> None:
-        """Pick (g_fwd, g_bwd) for this model, or fall back to 'dmma' (see the comment above)."""
+        """Pick (g_fwd, g_bwd) and the variance-collapse limit for this model, or fall back to 'dmma' (see the comment above)."""
+        import math
+
         forced = settings.int8_slices.value()
-        if forced is not None:  # developer / benchmark override: fixed slice counts, no probe
+        if forced is not None:  # developer / benchmark override: fixed slice counts, no probe, no variance-collapse re-routing
             if not (self._int8_exact(max(forced))):
                 raise _lib.McacqError("settings.int8_slices: train set too large for exact int32 slice products")
             self._set_slices(int(forced[0]), int(forced[1]))
             return
         probe = self._probe_points(Xt)
+        n_box = 256
         self.desc.contraction = 0
         v64, g64 = self._probe_variance_and_grad(probe)
-        floor = 1e-8 * self.y_std * self.y_std * self.outputscale
+        prior = self.y_std * self.y_std * self.outputscale
+        ratio64 = (v64 / prior).clamp_min(0.0)          # how far the variance has collapsed at each probe point
         gmax = g64.abs().max().clamp_min(1e-300)
         chosen_f = None
         err = gerr = float("inf")
@@ -208,12 +244,28 @@ class DevicePredictionStrategy:
                 break
             self._set_slices(gf, self.G_BWD_LADDER[0])
             v8, _ = self._probe_variance_and_grad(probe, backward=False)
-            err = float(((v8 - v64).abs() / v64.abs().clamp_min(floor)).max())
-            if err <= self.INT8_PROBE_TOL:
+            delta = float(((v8 - v64).abs() / prior).max())          # absolute accuracy as a fraction of the prior variance
+            # every point whose variance is at least `ratio_limit` of the prior is then within INT8_PROBE_TOL relatively (which
+            # is itself 4x inside the 1e-9 bar); points below it are re-evaluated through the FP64 contraction at run time
+            ratio_limit = min(1.0, delta / self.INT8_PROBE_TOL)
+            keep = ratio64 >= ratio_limit
+            rel = (v8 - v64).abs() / v64.abs().clamp_min(1e-300)
+            # usable only if the ordinary evaluation points (the uniform box probes) stay on the int8 path
+            box_ok = bool(keep[-n_box:].all())
+            err = float(rel[keep].max()) if (box_ok and bool(keep.any())) else float(rel[-n_box:].max())
+            if os.environ.get("MCACQ_PROBE_DEBUG"):
+                print(f"[int8 probe] G_fwd={gf}: delta={delta:.3e} ratio_limit={ratio_limit:.3e} box ratio min={float(ratio64[-n_box:].min()):.3e} "
+                      f"train ratio min={float(ratio64[:-n_box].min()):.3e} box_ok={box_ok} err={err:.3e} "
+                      f"box rel max={float(rel[-n_box:].max()):.3e} argmax delta idx={int(((v8 - v64).abs()).argmax())} of {probe.shape[0]}")
+            if box_ok and err <= self.INT8_PROBE_TOL:
                 chosen_f = gf
+                self.int8_var_ratio_limit = ratio_limit
+                # status-word byte floor(-4 log2 ratio): ratio < limit  =>  byte >= floor(-4 log2 limit)
+                self.int8_var_byte_limit = (int(math.floor(-4.0 * math.log2(ratio_limit))) - 1) if ratio_limit > 0.0 else 255
                 break
         chosen_b = None
         if chosen_f is not None:
+            keep_rows = (ratio64 >= self.int8_var_ratio_limit)
             pairs, pair_gc = self._pair_probe(probe)
             self.desc.contraction = 0
             _, gp64 = self._probe_blocks(pairs, pair_gc)
@@ -224,7 +276,8 @@ class DevicePredictionStrategy:
                 self._set_slices(chosen_f, gb)
                 _, g8 = self._probe_variance_and_grad(probe)
                 _, gp8 = self._probe_blocks(pairs, pair_gc)
-                gerr = max(float((g8 - g64).abs().max() / gmax), float((gp8 - gp64).abs().max() / gpmax))
+                gerr = max(float((g8 - g64)[keep_rows].abs().max() / gmax) if bool(keep_rows.any()) else 0.0,
+                           float((gp8 - gp64).abs().max() / gpmax))
                 if gerr <= self.INT8_PROBE_GRAD_TOL:
                     chosen_b = gb
                     break
@@ -237,6 +290,7 @@ class DevicePredictionStrategy:
                "the FP64 contraction (ill-conditioned train covariance)")
         warnings.warn(f"int8 contraction disabled for this model: {why}; using 'dmma'.", NumericalWarning, stacklevel=3)
         self.contraction = "dmma"
+        self.int8_var_ratio_limit, self.int8_var_byte_limit = None, None
         self.Rt_slices = self.Rt_scale = self.R_slices = self.R_scale = None
         self.desc.contraction = 0
         self.desc.Rt_slices = self.desc.Rt_scale = self.desc.R_slices = self.desc.R_scale = None

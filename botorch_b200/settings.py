@@ -13,6 +13,9 @@ is executed:
               q-batch's conditional covariance) exceeds this limit are re-evaluated through the FP64 contraction; "auto" = the
               library's calibrated limit (`DevicePredictionStrategy.INT8_COND_LIMIT`), None = never re-route.
 
+`int8_max_slices`: evaluate with the most accurate int8 slice counts (7 / 7) instead of the per-model ladder choice; set by the
+              L-BFGS-B drivers around their (small, latency-bound) evaluations.
+
 `optimizer` selects what `optimize_acqf` uses when no `gen_candidates` is passed:
   * "scipy"  -- `gen_candidates_scipy`: scipy's own L-BFGS-B routine stepped on the host (iterates bit-identical to
                 `scipy.optimize.minimize` per restart, as in the reference), one fused forward+backward per round;
@@ -51,4 +54,5 @@ class _Flag:
 contraction = _Flag("int8")
 int8_slices = _Flag(None)
 int8_cond_limit = _Flag("auto")
+int8_max_slices = _Flag(False)
 optimizer = _Flag("scipy")

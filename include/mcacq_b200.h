@@ -62,6 +62,10 @@ extern "C" {
  * fraction of a point's posterior variance left after conditioning on the baseline draws and the preceding points).   */
 #define MCACQ_INFO_COND_SHIFT 8
 #define MCACQ_INFO_COND_MASK 0xFF00
+/* bits 16..23: variance collapse of the q-batch, floor(-4 log2 min_i Sxx_ii / prior) saturated at 255 (prior = outputscale *
+ * y_std^2): how many digits the difference prior - |a|^2 has lost.                                                     */
+#define MCACQ_INFO_VAR_SHIFT 16
+#define MCACQ_INFO_VAR_MASK 0xFF0000
 
 /* Fitted-model operands (gpytorch DefaultPredictionStrategy caches + BoTorch transforms).   */
 typedef struct {
@@ -229,6 +233,10 @@ int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline* base, cons
 int mcacq_sample_reduce_forward(const mcacq_baseline* base, const mcacq_mc* mc, const double* mean, const double* Sxx,
                                 const double* Sxb, int64_t b, int q, double* acq, int32_t* info, double* Bm, double* Cm,
                                 void* stream);
+
+/* out3[0] = OR of the flag bits, out3[1] = largest conditioning byte, out3[2] = largest variance-collapse byte of the b status
+ * words of mcacq_acq_forward (one small launch; the caller reads 12 bytes instead of scanning info[]).                  */
+int mcacq_info_summary(const int32_t* info, int64_t b, int32_t* out3, void* stream);
 
 /* grad_X[b x q x d] = d( sum_b grad_acq[b] * acq[b] ) / dX.                                  */
 int mcacq_acq_backward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc, const double* X,

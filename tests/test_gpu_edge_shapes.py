@@ -138,7 +138,7 @@ def test_int8_guard_falls_back_on_ill_conditioned_models():
         with warnings.catch_warnings(record=True) as ws:
             warnings.simplefilter("always")
             strat = smooth.prediction_strategy()
-        assert strat.contraction == "dmma" and strat.int8_probe_error > strat.INT8_PROBE_TOL
+        assert strat.contraction == "dmma" and strat.int8_var_ratio_limit is None
         assert any(issubclass(w.category, NumericalWarning) and "int8" in str(w.message) for w in ws)
         rough = SingleTaskGP(X.to(DEV), Y.to(DEV), covar_module=RBFKernel(ard_num_dims=1, lengthscale=torch.tensor([0.02]))).to(DEV)
         rough.likelihood.noise = 1e-2

@@ -44,6 +44,10 @@ def test_posterior_and_acquisition_at_training_points_full_size(cfg, mode):
         assert strat.contraction == mode    # no silent fall-back on the benchmark problems
         if mode == "int8":
             assert strat.int8_probe_error <= strat.INT8_PROBE_TOL and strat.g_fwd in strat.G_FWD_LADDER
+            assert strat.int8_var_ratio_limit is not None and 0.0 < strat.int8_var_ratio_limit < 0.05
+        from botorch_b200.acquisition._fused import RerouteStats
+
+        RerouteStats.q_batches = RerouteStats.calls = 0
         for delta in DELTAS:
             P = _near_train(data, 48, delta)
             post = model.posterior(P.unsqueeze(1).to(DEV))
@@ -62,11 +66,22 @@ def test_posterior_and_acquisition_at_training_points_full_size(cfg, mode):
             rel = ((val.detach().cpu() - v_o).abs() / v_o.abs()).max()
             assert float(rel) < 1e-9, (cfg, mode, delta, float(rel))
             assert float((gr.cpu() - g_o).abs().max() / g_o.abs().max()) < 1e-6, (cfg, mode, delta)
+        # the int8 mode holds the bar at the training points BECAUSE it recognises them (variance-collapse byte of the status
+        # word) and evaluates those q-batches through the FP64 contraction; ordinary Sobol points stay on the int8 path
+        if mode == "int8":
+            assert RerouteStats.q_batches > 0
+            RerouteStats.q_batches = RerouteStats.calls = 0
+            Xs = configs.eval_points(data, 256).to(DEV)
+            with torch.no_grad():
+                acqf(Xs)
+            assert RerouteStats.q_batches <= 2     # (the 99.9 % quantile of the sweep's collapse byte sits at the limit)
+        else:
+            assert RerouteStats.q_batches == 0
 
 
-def test_int8_slice_ladder_picks_more_slices_only_where_needed():
-    """The probe is per fitted model: the benchmark models need the 7th forward slice at their training points; a smooth,
-    well-conditioned toy model keeps 6."""
+def test_int8_slice_ladder_and_collapse_limit_per_model():
+    """The probe is per fitted model.  The benchmark models keep 6 forward slices for ordinary points (their variance-collapse
+    limit is ~1 % of the prior; the training points lie below it and take the FP64 route)."""
     from botorch_b200 import settings
     from botorch_b200.benchmarks import configs
     from botorch_b200.models import RBFKernel, SingleTaskGP
@@ -74,7 +89,18 @@ def test_int8_slice_ladder_picks_more_slices_only_where_needed():
     with settings.contraction("int8"):
         data = configs.make_problem(configs.C2)
         strat = configs.build_model(data, DEV).prediction_strategy()
-        assert (strat.contraction, strat.g_fwd) == ("int8", 7) and strat.int8_probe_error <= 2.5e-10
+        assert strat.contraction == "int8" and strat.g_fwd == 6 and strat.int8_probe_error <= 2.5e-10
+        assert 1e-4 < strat.int8_var_ratio_limit < 0.05 and 17 <= strat.int8_var_byte_limit <= 53
+        # the posterior API applies the same rule: variances AT training points to 1e-9 although G = 6 alone gives ~4e-9
+        from oracle.harness import build_oracle
+
+        P = data.train_X[:64].unsqueeze(1)
+        v = configs.build_model(data, DEV).posterior(P.to(DEV)).variance.reshape(-1).cpu()
+        _, c_o = build_oracle(data).gp.posterior_mvn(P)
+        assert float(((v - c_o.reshape(-1)).abs() / c_o.reshape(-1)).max()) < 1e-9
+        # the CUDA-graph rounds of the device optimiser cannot re-route: they run the most accurate slice counts
+        mv = strat.max_slices_view()
+        assert (mv.g_fwd, mv.g_bwd) == (7, 7) and mv.int8_var_byte_limit is None and mv.desc.g_fwd == 7
         g = torch.Generator().manual_seed(0)
         X = torch.rand(40, 2, generator=g, dtype=torch.float64)
         Y = torch.sin(3 * X.sum(-1, keepdim=True))

@@ -24,6 +24,9 @@ for cfg in ("C1", "C2", "C3"):
     cond = ((info >> 8) & 0xFF).cpu()
     qs = torch.quantile(cond.double(), torch.tensor([0.0, 0.5, 0.9, 0.99, 0.999, 1.0], dtype=torch.float64)).tolist()
     print(f"{cfg}: mode {strat.contraction}({strat.g_fwd},{strat.g_bwd}) sweep cond byte min/50/90/99/99.9/max = {qs}  (rho_min = {2 ** (-qs[-1] / 4):.3e})")
+    vb = ((info >> 16) & 0xFF).cpu()
+    qv = torch.quantile(vb.double(), torch.tensor([0.0, 0.5, 0.9, 0.99, 0.999, 1.0], dtype=torch.float64)).tolist()
+    print(f"    variance-collapse byte min/50/90/99/99.9/max = {qv} (smallest var/prior = {2 ** (-qv[-1] / 4):.3e}); model limit: ratio {strat.int8_var_ratio_limit} byte {strat.int8_var_byte_limit}; probe err {strat.int8_probe_error:.2e} grad {strat.int8_probe_grad_error:.2e}")
     ob = torch.stack([torch.zeros(spec.d), torch.ones(spec.d)]).to(dev, torch.float64)
     RerouteStats.q_batches = RerouteStats.calls = 0
     cand, val = optimize_acqf(acqf, bounds=ob, q=spec.q, num_restarts=spec.num_restarts, raw_samples=min(spec.raw_samples, 8192),
