@@ -181,7 +181,7 @@ def main():
         raise SystemExit("bench.py: CUDA is required (botorch_b200 has no CPU path)")
     import torch.distributed as dist
     from botorch_b200 import _lib
-    from botorch_b200.acquisition._fused import LaunchStats
+    from botorch_b200.acquisition._fused import LaunchStats, RerouteStats
     from botorch_b200.optim.sharded import all_gather_values, shard_bounds
 
     torch.cuda.set_device(local_rank)
@@ -253,12 +253,14 @@ def main():
             for _ in range(max(args.warmup, 3)):
                 step_resident()
             LaunchStats.launches = 0
+            RerouteStats.q_batches = RerouteStats.calls = 0
             clocks = ClockSampler(local_rank) if with_clocks else None
             if clocks:
                 clocks.start()
             ms_total = timed(step_resident, args.steps)
             clock_info = clocks.stop() if clocks else None
             launches = LaunchStats.launches
+            rerouted = RerouteStats.q_batches
             for _ in range(2):
                 step_e2e()
             ms_e2e = timed(step_e2e, args.steps)
@@ -276,9 +278,11 @@ def main():
                 nr = max(1, min(spec.num_restarts, b_local))
 
                 def step_round():
-                    Xc = X_dev[:nr].detach().requires_grad_(True)
-                    v = acqf(Xc)
-                    torch.autograd.grad(v.sum(), Xc)
+                    # as gen_candidates_scipy evaluates a round (generation/gen.py): the int8 mode's most accurate slice counts
+                    with settings.int8_max_slices(True):
+                        Xc = X_dev[:nr].detach().requires_grad_(True)
+                        v = acqf(Xc)
+                        torch.autograd.grad(v.sum(), Xc)
 
                 for _ in range(3):
                     step_round()
@@ -317,7 +321,7 @@ def main():
                           "sweep_forward_only_ms_per_step": ms_fwd / args.steps,
                           "lbfgs_round": {"q_batches": nr, "ms_per_fwd_bwd_call": ms_round,
                                           "note": "per rank, not sharded: one optimiser round over num_restarts q-batches"}}
-        return {"model": model, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "clocks": clock_info,
+        return {"model": model, "ms_total": ms_total, "ms_e2e": ms_e2e, "launches": launches, "rerouted": rerouted, "clocks": clock_info,
                 "phases": phases}
 
     other = "dmma" if args.contraction == "int8" else "int8"
@@ -457,9 +461,13 @@ def main():
                            "l2": "inputs larger than L2 (per-chunk working set %.1f GB)" % (2 * chunk * spec.q * model.prediction_strategy().np * 8 / 1e9),
                            "parallelism": f"shard b over {world} GPU(s), all-gather of values",
                            "contraction": (("int8 (library default): Ozaki split of the fp64 contraction onto the INT8 tensor cores "
-                                            "(tcgen05); %d forward / %d backward signed 8-bit slices picked by the per-model "
-                                            "probe at the training points (variance within 2.5e-10 of the FP64 contraction)"
-                                            % (model.prediction_strategy().g_fwd, model.prediction_strategy().g_bwd))
+                                            "(tcgen05); %d forward / %d backward signed 8-bit slices picked by the per-model probe; "
+                                            "q-batches whose variance has collapsed below %.3g of the prior (at / next to training "
+                                            "points) or whose conditional covariance is nearly singular are re-evaluated through the "
+                                            "FP64 DMMA contraction: %d of %d q-batches in the timed steps"
+                                            % (model.prediction_strategy().g_fwd, model.prediction_strategy().g_bwd,
+                                               model.prediction_strategy().int8_var_ratio_limit or 0.0, head["rerouted"],
+                                               b_total * args.steps))
                                            if model.prediction_strategy().contraction == "int8" else "dmma: FP64 DMMA tensor-core kernel")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b_total * spec.q * spec.d * 8,
                         "d2h_bytes_per_step": b_total * 8 + b_total * spec.q * spec.d * 8, "ms_per_step": ms_e2e / args.steps},

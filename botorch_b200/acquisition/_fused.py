@@ -89,6 +89,7 @@ def _info_summary(info: Tensor) -> tuple[int, int, int]:
         return 0, 0, 0
     out = torch.empty(3, dtype=torch.int32, device=info.device)
     _lib.check(_lib.lib().mcacq_info_summary(info.data_ptr(), info.numel(), out.data_ptr(), _lib.stream_ptr()), "mcacq_info_summary")
+    LaunchStats.launches += 1
     flags, cond, vbyte = out.tolist()
     return int(flags), int(cond), int(vbyte)
 

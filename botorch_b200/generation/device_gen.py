@@ -163,7 +163,7 @@ def _cached_round(acqf, opt: DeviceLBFGSB, clamped: Tensor, q: int, d: int, opti
     optimiser state) is kept on the acquisition function and re-used by later calls with the same shapes, operands and
     L-BFGS-B options (sequential greedy optimisation, retries, repeated `optimize_acqf` calls)."""
     use_graph = bool(options.get("cuda_graph", True))
-    strat = acqf.model.prediction_strategy()
+    strat = acqf.model.prediction_strategy().max_slices_view()   # (what _FusedRound runs; cached on the strategy)
     base = acqf._baseline_operands() if hasattr(acqf, "_baseline_operands") else None
     mc = acqf._mc_operands(opt.X.view(opt.N, q, d))
     key = (opt.N, q, d, opt.maxiter, opt.maxfun, opt.factr, opt.pgtol, opt.maxls, use_graph, id(strat), id(base), id(mc),
