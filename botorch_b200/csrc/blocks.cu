@@ -277,7 +277,7 @@ posterior_blocks_kernel(BlocksParams p) {
 // overestimates rows whose terms cancel -- nearly collinear rows of A with alternating coefficients, i.e. exactly the
 // ill-conditioned q-batches -- by the inverse of the smallest relative pivot, and every factor 256 costs one slice.
 template <int QT, int RT, int PASS>
-__global__ void __launch_bounds__(BLK_WARPS * 32)
+__global__ void __launch_bounds__(BLK_WARPS * 32, (QT == 1 && RT <= 2) ? 4 : 1)
 posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
@@ -417,13 +417,14 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
                 if (NT == 4) Y[e][t] = y; else Y[0][e * 2 + t] = y;
               }
             int8_t* sdst = p.slices + ((size_t)(bb * q + i)) * np + oc;
-            for (int pp = 0; pp < p.G; pp++) {
-              if (NT == 4)
-                *reinterpret_cast<uint2*>(sdst + pp * slice_stride) =
-                    make_uint2(pack_digit4(Y[0], p.G - 1 - pp), pack_digit4(Y[1], p.G - 1 - pp));
-              else
-                *reinterpret_cast<unsigned*>(sdst + pp * slice_stride) = pack_digit4(Y[0], p.G - 1 - pp);
-            }
+            if (NT == 4)
+              digits4x2(Y[0], Y[1], [&](int dg, unsigned wa, unsigned wb) {
+                if (dg < p.G) *reinterpret_cast<uint2*>(sdst + (size_t)(p.G - 1 - dg) * slice_stride) = make_uint2(wa, wb);
+              });
+            else
+              digits4(Y[0], [&](int dg, unsigned w) {
+                if (dg < p.G) *reinterpret_cast<unsigned*>(sdst + (size_t)(p.G - 1 - dg) * slice_stride) = w;
+              });
           } else {
             double* dst = Ab + (int64_t)i * np + oc;
 #pragma unroll

@@ -65,6 +65,8 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
     s1[k * CT + p] = (gr < m1) ? U1[gr * d + k] : 0.0;
   }
   double pm[4] = {0.0, 0.0, 0.0, 0.0};
+  // 2^(8G - 2 - e): |shift| stays far inside the exponent range (0 < outputscale < 2^e is a kernel hyper-parameter)
+  const double slice_mul = SLICES ? ldexp(1.0, 8 * G - 2 - fixed_exp) : 1.0;
 
   for (int ct = t_begin; ct < t_end; ct++) {
     const int col0 = ct * CT;
@@ -112,12 +114,14 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
 #pragma unroll
         for (int j = 0; j < 4; j++) pm[i] = fma(v[j], (gc0 + j < m2) ? alpha[gc0 + j] : 0.0, pm[i]);
         if (gc0 < ldk) {  // ldk is a multiple of 16, so the 4 columns are all inside the pitch
-          const int shift = 8 * G - 2 - fixed_exp;
           unsigned long long Y[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) Y[j] = balanced_bytes(__double2ll_rn(ldexp(v[j], shift)));
-          for (int pp = 0; pp < G; pp++)  // slice pp = digit G-1-pp (most significant first)
-            *reinterpret_cast<unsigned*>(S + ((size_t)pp * m1_total + row_base + gr) * ldk + gc0) = pack_digit4(Y, G - 1 - pp);
+          for (int j = 0; j < 4; j++) Y[j] = balanced_bytes(__double2ll_rn(v[j] * slice_mul));   // exact: a power of two
+          int8_t* sdst = S + ((size_t)row_base + gr) * ldk + gc0;
+          const size_t sstride = (size_t)m1_total * ldk;
+          digits4(Y, [&](int dg, unsigned w) {  // slice pp = digit G-1-pp (most significant first)
+            if (dg < G) *reinterpret_cast<unsigned*>(sdst + (size_t)(G - 1 - dg) * sstride) = w;
+          });
         }
         continue;
       }

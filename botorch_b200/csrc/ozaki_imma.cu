@@ -810,7 +810,9 @@ slice_rows_kernel(const double* __restrict__ X, int64_t rows, int K, int64_t ldx
       X = X > lim ? lim : (X < -lim ? -lim : X);
       Y[j] = balanced_bytes(X);
     }
-    for (int p = 0; p < G; p++) *reinterpret_cast<unsigned*>(out + p * slice_stride + k0) = pack_digit4(Y, G - 1 - p);
+    digits4(Y, [&](int dg, unsigned w) {
+      if (dg < G) *reinterpret_cast<unsigned*>(out + (size_t)(G - 1 - dg) * slice_stride + k0) = w;
+    });
   }
 }
 
