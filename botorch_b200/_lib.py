@@ -72,7 +72,7 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_slice_rows",
+    "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_log_hvi_forward", "mcacq_log_hvi_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
     "mcacq_sample_reduce_forward", "mcacq_info_summary", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
 ]
@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
     L.mcacq_workspace_bytes_model.restype = sz
     L.mcacq_sample_reduce_forward.argtypes = [C.POINTER(Baseline), C.POINTER(MC), vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_info_summary.argtypes = [vp, i64, vp, vp]
+    L.mcacq_log_hvi_forward.argtypes = [vp, vp, vp, i64, i32, i32, i32, dbl, dbl, vp, vp, vp]
+    L.mcacq_log_hvi_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, vp, vp, vp]
     L.mcacq_lbfgsb_state_bytes.argtypes = [i64, i32]
     L.mcacq_lbfgsb_state_bytes.restype = sz
     L.mcacq_lbfgsb_init.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp]

@@ -67,3 +67,46 @@ class _FusedLogAreasCUDA(torch.autograd.Function):
 
 def fused_log_areas(obj_subsets: Tensor, cell_lower: Tensor, cell_upper: Tensor, tau_relu: float, tau_max: float) -> Tensor:
     return _FusedLogAreasCUDA.apply(obj_subsets, cell_lower, cell_upper, tau_relu, tau_max)
+
+
+class _FusedLogHVI(torch.autograd.Function):
+    """Per-sample log hypervolume improvement in ONE launch (csrc/log_hvi.cu): obj (B, q, m) -> (B,)."""
+
+    @staticmethod
+    def forward(ctx, obj: Tensor, cell_lower: Tensor, cell_upper: Tensor, tau_relu: float, tau_max: float):
+        o = obj.detach().contiguous()
+        cl = cell_lower.detach().to(o).contiguous()
+        cu = cell_upper.detach().to(o).contiguous()
+        _lib.require_cuda(o, "obj")
+        B, q, m = o.shape
+        out = torch.empty(B, dtype=torch.float64, device=o.device)
+        lcl = torch.empty_like(cl)
+        rc = _lib.lib().mcacq_log_hvi_forward(o.data_ptr(), cl.data_ptr(), cu.data_ptr(), B, q, m, cl.shape[-2], float(tau_relu),
+                                              float(tau_max), out.data_ptr(), lcl.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "mcacq_log_hvi_forward")
+        ctx.save_for_backward(o, cl, cu, out)
+        ctx.taus = (float(tau_relu), float(tau_max))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        o, cl, cu, out = ctx.saved_tensors
+        B, q, m = o.shape
+        go = grad_out.to(o).contiguous()
+        g_obj = torch.empty_like(o)
+        lcl = torch.empty_like(cl)
+        rc = _lib.lib().mcacq_log_hvi_backward(go.data_ptr(), out.data_ptr(), o.data_ptr(), cl.data_ptr(), cu.data_ptr(), B, q, m,
+                                               cl.shape[-2], ctx.taus[0], ctx.taus[1], g_obj.data_ptr(), lcl.data_ptr(),
+                                               _lib.stream_ptr())
+        _lib.check(rc, "mcacq_log_hvi_backward")
+        return g_obj, None, None, None, None
+
+
+def log_hvi_fusable(obj: Tensor, cell_lower: Tensor) -> bool:
+    return (obj.is_cuda and obj.dtype == torch.float64 and obj.dim() == 3 and obj.shape[-2] <= 6 and obj.shape[-1] <= 4
+            and cell_lower.dim() == 2)
+
+
+def fused_log_hvi(obj: Tensor, cell_lower: Tensor, cell_upper: Tensor, tau_relu: float, tau_max: float) -> Tensor:
+    """obj (B, q, m) -> per-sample log HVI (B,), differentiable w.r.t. obj."""
+    return _FusedLogHVI.apply(obj, cell_lower, cell_upper, tau_relu, tau_max)

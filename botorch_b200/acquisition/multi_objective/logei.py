@@ -19,7 +19,8 @@ from ...utils.safe_math import logdiffexp, logmeanexp, logplusexp, logsumexp
 from ...utils.transforms import concatenate_pending_points, t_batch_mode_transform
 from ..acquisition import AcquisitionFunction, MCSamplerMixin
 from ..logei import TAU_MAX, TAU_RELU, check_tau
-from .fused_log_areas import fused_log_areas
+from ... import settings
+from .fused_log_areas import fused_log_areas, fused_log_hvi, log_hvi_fusable
 
 
 def compute_subset_indices(q: int, device=None) -> dict[str, Tensor]:
@@ -60,6 +61,11 @@ class qLogExpectedHypervolumeImprovement(AcquisitionFunction, MCSamplerMixin):
     def _compute_log_qehvi(self, samples: Tensor, X: Tensor | None = None) -> Tensor:
         obj = samples  # mc_samples x batch_shape x q x m  (identity multi-output objective)
         q = obj.shape[-2]
+        flat3 = obj.reshape(-1, q, obj.shape[-1])
+        if settings.fused_log_hvi.value() and log_hvi_fusable(flat3, self.cell_lower_bounds):
+            # steps 1-8 in one launch: every li[j][k] once per cell, subsets as bit masks, streaming log-sum-exps
+            per_sample = fused_log_hvi(flat3, self.cell_lower_bounds, self.cell_upper_bounds, self.tau_relu, self.tau_max)
+            return logmeanexp(per_sample.view(obj.shape[:-2]), dim=0)
         idx = self.compute_q_subset_indices(q_out=q, device=obj.device)
         batch_shape = obj.shape[:-2]
         nc = self.cell_lower_bounds.shape[-2]

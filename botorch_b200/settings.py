@@ -55,4 +55,5 @@ contraction = _Flag("int8")
 int8_slices = _Flag(None)
 int8_cond_limit = _Flag("auto")
 int8_max_slices = _Flag(False)
+fused_log_hvi = _Flag(True)   # qLogEHVI: one fused kernel for the inclusion-exclusion loop (False: per-subset-size kernels)
 optimizer = _Flag("scipy")

@@ -258,6 +258,17 @@ int mcacq_log_areas_backward(const void* grad_out, const void* obj_subsets, cons
                              int dtype, double tau_relu, double tau_max, void* grad_obj, void* lcl_workspace,
                              void* stream);
 
+/* The whole inclusion-exclusion loop of `_compute_log_qehvi` (botorch/acquisition/multi_objective/logei.py:272-435, steps
+ * 1-8) for B MC samples in one launch: obj [B x q x m] (objective samples of the q points), cell bounds [nc x m] ->
+ * out[B] = logsumexp_cells logdiffexp(even-size subsets, odd-size subsets) of the log-areas; q <= 6, m <= 4, fp64.  Same
+ * building blocks (log_fatplus, fatmin, upper-bound clamp) as mcacq_log_areas_*, each li[j][k] evaluated once per cell
+ * instead of once per subset membership.  Backward: grad_out [B], out [B] (from the forward) -> grad_obj [B x q x m].      */
+int mcacq_log_hvi_forward(const double* obj, const double* cell_lower, const double* cell_upper, int64_t B, int q, int m,
+                          int nc, double tau_relu, double tau_max, double* out, double* lcl_workspace, void* stream);
+int mcacq_log_hvi_backward(const double* grad_out, const double* out, const double* obj, const double* cell_lower,
+                           const double* cell_upper, int64_t B, int q, int m, int nc, double tau_relu, double tau_max,
+                           double* grad_obj, double* lcl_workspace, void* stream);
+
 /* Scrambled-Sobol points straight on the device: out[k][j] = (shift[j] XOR_{b in gray(first_index + k)} sobolstate[j][b]) * 2^-30,
  * gray(i) = i ^ (i >> 1) -- the closed form of the sequence `torch.quasirandom.SobolEngine.draw` produces point by point
  * (botorch/utils/sampling.py:74-111 `draw_sobol_samples`, called by gen_batch_initial_conditions, optim/initializers.py:425-447).

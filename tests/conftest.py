@@ -53,3 +53,4 @@ def _restore_settings():
     settings.int8_slices.set(saved[1])
     settings.int8_cond_limit.set(saved[2])
     settings.int8_max_slices.set(False)
+    settings.fused_log_hvi.set(True)

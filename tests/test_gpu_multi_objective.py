@@ -56,3 +56,42 @@ def test_model_list_posterior_shapes():
     for k, gp in enumerate(orc.gps):
         m_o, c_o = gp.posterior_mvn(Xq)
         assert float((post.mean[..., k].cpu() - m_o).abs().max() / m_o.abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("q,m,nc", [(1, 2, 5), (2, 3, 7), (3, 4, 12), (4, 4, 32), (5, 2, 9), (6, 3, 4)])
+def test_fused_log_hvi_kernel_equals_the_per_subset_size_route(q, m, nc):
+    """csrc/log_hvi.cu (one launch: subsets as bit masks, streaming log-sum-exps) against the route that mirrors the reference
+    step by step (per-subset-size `fused_log_areas` launches + safe_math reductions): per-sample values and gradients w.r.t.
+    the objective samples, incl. a cell with an infinite upper bound and samples far below / above the cells."""
+    from botorch_b200.acquisition.multi_objective.fused_log_areas import fused_log_hvi
+    from botorch_b200.acquisition.multi_objective.logei import qLogExpectedHypervolumeImprovement
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(10 * q + m)
+    lo = torch.randn(nc, m, generator=g, dtype=torch.float64) * 0.5 - 0.5
+    hi = lo + torch.rand(nc, m, generator=g, dtype=torch.float64) + 0.1
+    hi[-1] = float("inf")
+    B = 257
+    obj = torch.randn(B, q, m, generator=g, dtype=torch.float64)
+    obj[0] = -40.0          # far below every cell: log_fatplus deep in its tail
+    obj[1] = 40.0           # far above
+    obj[2, 0] = obj[2, -1]  # tie between two points
+    acqf = qLogExpectedHypervolumeImprovement.__new__(qLogExpectedHypervolumeImprovement)
+    torch.nn.Module.__init__(acqf)
+    acqf.register_buffer("cell_lower_bounds", lo.to(dev))
+    acqf.register_buffer("cell_upper_bounds", hi.to(dev))
+    acqf.tau_relu, acqf.tau_max, acqf.q_out, acqf.q_subset_indices = 1e-6, 1e-2, -1, {}
+    from botorch_b200 import settings
+
+    o1 = obj.to(dev).requires_grad_(True)
+    v1 = fused_log_hvi(o1, lo.to(dev), hi.to(dev), 1e-6, 1e-2)
+    w = torch.randn(B, generator=g, dtype=torch.float64).to(dev)
+    (g1,) = torch.autograd.grad((v1 * w).sum(), o1)
+    o2 = obj.to(dev).requires_grad_(True)
+    with settings.fused_log_hvi(False):
+        # the reference-shaped route reduces over dim 0 at the end (logmeanexp over S = 1 is the identity)
+        v2 = acqf._compute_log_qehvi(o2.unsqueeze(0).transpose(0, 1).reshape(1, B, q, m))
+    (g2,) = torch.autograd.grad((v2 * w).sum(), o2)
+    assert torch.isfinite(v1).all() and torch.isfinite(g1).all()
+    assert float(((v1 - v2).abs() / v2.abs().clamp_min(1e-12)).max()) < 1e-11
+    assert float((g1 - g2).abs().max() / g2.abs().max()) < 1e-10
