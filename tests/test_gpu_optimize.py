@@ -49,6 +49,25 @@ def test_initial_condition_indices_bit_exact():
         assert torch.equal(ics_gpu.cpu(), ics_cpu)  # same Sobol rows selected, in the same order
 
 
+@pytest.mark.parametrize("cfg,raw,nr,S", [("C2", 8192, 64, 256), ("C3", 2048, 64, 256)])
+def test_initial_condition_indices_bit_exact_at_benchmark_sizes(cfg, raw, nr, S):
+    """the selected Sobol rows at the C2 sweep size (raw_samples = 8192, n = 1024) and on the full-size C3
+    model (n = 4096, raw sweep shrunk to what the CPU oracle evaluates in seconds), library default (int8) mode: Boltzmann
+    sampling and top-n both pick bit-identical rows from CUDA and oracle values."""
+    from botorch_b200.optim import gen_batch_initial_conditions
+
+    data, acqf, oracle, dev = _problem(cfg, S=S)
+    q = data.spec.q
+    for opts in ({"seed": 0}, {"seed": 3, "topn": True}):
+        torch.manual_seed(0)
+        ics_gpu = gen_batch_initial_conditions(acqf, data.bounds.to(dev), q=q, num_restarts=nr, raw_samples=raw, options=opts)
+        torch.manual_seed(0)
+        ics_cpu = gen_batch_initial_conditions(oracle, data.bounds, q=q, num_restarts=nr, raw_samples=raw,
+                                               options={**opts, "init_batch_limit": 256})
+        assert ics_gpu.shape == (nr, q, data.spec.d)
+        assert torch.equal(ics_gpu.cpu(), ics_cpu)
+
+
 def test_optimize_acqf_candidates_match_oracle():
     from botorch_b200.optim import optimize_acqf
 
