@@ -18,5 +18,11 @@ parts are restated from the published gpytorch 1.15 / linear_operator 0.6 algori
 are pinned: `tests/test_oracle_golden.py` checks the restatements against the
 reference modules imported from `/root/reference` (when present), and
 `tests/golden/` holds vectors generated from those reference modules
-(`tests/golden/make_golden.py`).
+(`tests/golden/make_golden.py`).  Against an INDEPENDENT implementation of the same
+published algorithm the GP part IS pinned: `tests/test_oracle_vs_sklearn.py` compares
+posterior mean, full covariance, the train Cholesky factor and `(K + noise)^-1 y` with
+scikit-learn's `GaussianProcessRegressor` (fixed hyper-parameters, ARD RBF / Matern-5/2,
+ScaleKernel, Normalize, Standardize, homo- / heteroskedastic noise) to 1e-9, and
+`tests/test_real_botorch_probe.py` compares the oracle with a real BoTorch + gpytorch
+install at 1e-12 wherever one is importable (it skips, visibly, where none is).
 """

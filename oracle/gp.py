@@ -1,6 +1,7 @@
 """Exact-GP posterior restatement (gpytorch ExactGP eval path as configured by BoTorch).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: gpytorch>=1.15.2 and
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED against gpytorch itself (pinned to
+scikit-learn's GaussianProcessRegressor instead, tests/test_oracle_vs_sklearn.py): gpytorch>=1.15.2 and
 linear_operator>=0.6.1 are not vendored under /root/reference and not installable here; the
 functions below restate their published algorithms as BoTorch configures them:
 
