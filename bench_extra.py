@@ -183,7 +183,7 @@ def run_c4(args, ClockSampler, impl_reference=False):
         ph["cholesky N x N (cuSOLVER potrf, library)"] = _event_ms(lambda: psd_safe_cholesky(covar, max_tries=6))
         chol = psd_safe_cholesky(covar, max_tries=6)
         Z = torch.randn(ns, N, **f64)
-        ph["dgemm_nt   L z (TRMM)"] = _event_ms(lambda: strat.lower_times_samples(chol, Z))
+        ph["L z (lower_times_few, memory-bound row sweep)"] = _event_ms(lambda: strat.lower_times_samples(chol, Z))
         fp64_peak = _dgemm_peak(dev)
         syrk_flops = float(N) * (N + 1) * strat.np    # 2 flop per k over the N (N + 1) / 2 entries on and below the diagonal
         syrk_ms = ph["dgemm_nt   A A^T (SYRK)"]
@@ -207,7 +207,7 @@ def run_c4(args, ClockSampler, impl_reference=False):
                            "parallelism": f"{T} independent trust regions per GPU, {world} GPU(s), no data-path collective"},
                 "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": T * world * N * d * 8, "d2h_bytes_per_step": T * world * ns * d * 8,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": 6 * T * args.steps, "clocks": clock_info, "roofline": roofline,
+                "gpu_launches": 5 * T * args.steps, "clocks": clock_info, "roofline": roofline,
                 "phases_ms_per_trust_region": ph}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -72,7 +72,7 @@ _lib = None
 EXPORTS = [
     "mcacq_version", "mcacq_num_sms", "mcacq_scale_inputs", "mcacq_cov_cross", "mcacq_cov_cross_bwd",
     "mcacq_dgemm_tri", "mcacq_workspace_bytes", "mcacq_posterior", "mcacq_posterior_backward", "mcacq_acq_forward", "mcacq_acq_backward",
-    "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_log_hvi_forward", "mcacq_log_hvi_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_slice_rows",
+    "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_log_hvi_forward", "mcacq_log_hvi_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_lower_times_few", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
     "mcacq_sample_reduce_forward", "mcacq_info_summary", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
 ]
@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.mcacq_dgemm_tri.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_dgemm_nt.argtypes = [i32, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp]
     L.mcacq_syrk_sub.argtypes = [i64, i32, vp, i64, vp, i64, dbl, vp, vp]
+    L.mcacq_lower_times_few.argtypes = [i64, i32, vp, i64, vp, i64, vp, i64, vp]
     L.mcacq_cov_cross_sliced.argtypes = [i32, dbl, vp, i64, vp, i32, i32, i64, vp, i32, i32, vp, vp, vp]
     L.mcacq_slice_rows.argtypes = [vp, i64, i32, i64, i32, i32, i32, i32, vp, vp, vp]
     L.mcacq_ozaki_contract.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]

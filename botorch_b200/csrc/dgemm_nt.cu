@@ -149,6 +149,60 @@ dgemm_nt_kernel(int a_lower, int64_t M, int N, int K, const double* __restrict__
 static int dgemm_nt_launch(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt, int64_t ldb,
                            double* C, int64_t ldc, int32_t* tile_counter, double syrk_scale, void* stream);
 
+namespace mcacq {
+// Y[N x S] = L[N x N] Z[S x N]^T for a HANDFUL of sample vectors (S <= 8): a memory-bound sweep over the lower triangle of L.
+// One warp per row, lanes stride the row (coalesced 256-byte reads of L, Z stays in L1 / L2), the S dot products share every
+// L element; warp-shuffle tree at the end.  (The 64 x 64-tile DMMA kernel above spends a full tile on S = 4 columns.)
+template <int SMAX>
+__global__ void __launch_bounds__(256)
+lower_times_few_kernel(int64_t N, int S, const double* __restrict__ L, int64_t ldl, const double* __restrict__ Z, int64_t ldz,
+                       double* __restrict__ Y, int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  // heaviest (longest) rows first
+  const int64_t row = N - 1 - ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (row < 0) return;
+  double acc[SMAX];
+#pragma unroll
+  for (int s = 0; s < SMAX; s++) acc[s] = 0.0;
+  const double* lr = L + row * ldl;
+  int64_t k = lane;
+  for (; k + 96 <= row; k += 128) {   // four independent 256-byte row segments in flight per warp
+    const double l0 = lr[k], l1 = lr[k + 32], l2 = lr[k + 64], l3 = lr[k + 96];
+#pragma unroll
+    for (int s = 0; s < SMAX; s++)
+      if (s < S) {
+        const double* z = Z + s * ldz + k;
+        acc[s] = fma(l0, z[0], fma(l1, z[32], fma(l2, z[64], fma(l3, z[96], acc[s]))));
+      }
+  }
+  for (; k <= row; k += 32) {
+    const double l = lr[k];
+#pragma unroll
+    for (int s = 0; s < SMAX; s++)
+      if (s < S) acc[s] = fma(l, Z[s * ldz + k], acc[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < SMAX; s++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+    if (lane == 0 && s < S) Y[row * ldy + s] = acc[s];
+  }
+}
+}  // namespace mcacq
+
+extern "C" int mcacq_lower_times_few(int64_t N, int S, const double* L, int64_t ldl, const double* Z, int64_t ldz, double* Y,
+                                     int64_t ldy, void* stream) {
+  using namespace mcacq;
+  if (!L || !Z || !Y || N < 0 || S <= 0 || ldl < N || ldz < N || ldy < S) return MCACQ_EINVAL;
+  if (S > 8) return MCACQ_ELIMIT;
+  if (N == 0) return 0;
+  const unsigned blocks = (unsigned)((N + 7) / 8);
+  lower_times_few_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(N, S, L, ldl, Z, ldz, Y, ldy);
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_t lda, const double* Bt,
                               int64_t ldb, double* C, int64_t ldc, int32_t* tile_counter, void* stream) {
   if (a_lower != 0 && a_lower != 1) return MCACQ_EINVAL;

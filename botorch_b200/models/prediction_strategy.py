@@ -416,11 +416,16 @@ class DevicePredictionStrategy:
         """Y[N x S] = L[N x N] Z[S x N]^T with the triangular-aware DMMA kernel (MultivariateNormal.rsample's
         `root @ base_samples`)."""
         N, S = chol.shape[-1], Z.shape[0]
-        if N % 2:
-            raise _lib.McacqError("lower_times_samples needs an even number of points (16-byte row chunks)")
         chol = chol.contiguous()
         Z = Z.contiguous()
         Y = torch.empty(N, S, device=self.device, dtype=torch.float64)
+        if S <= 8:
+            # a handful of samples: memory-bound sweep over the triangle (one warp per row), any N
+            _lib.check(_lib.lib().mcacq_lower_times_few(N, S, chol.data_ptr(), N, Z.data_ptr(), N, Y.data_ptr(), S,
+                                                        _lib.stream_ptr()), "lower_times_few")
+            return Y
+        if N % 2:
+            raise _lib.McacqError("lower_times_samples needs an even number of points (16-byte row chunks)")
         counter = torch.zeros(64, dtype=torch.int32, device=self.device)
         _lib.check(_lib.lib().mcacq_dgemm_nt(1, N, S, N, chol.data_ptr(), N, Z.data_ptr(), N, Y.data_ptr(), S,
                                              counter.data_ptr(), _lib.stream_ptr()), "dgemm_nt (trmm)")

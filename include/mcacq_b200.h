@@ -193,6 +193,12 @@ int mcacq_dgemm_nt(int a_lower, int64_t M, int N, int K, const double* A, int64_
 int mcacq_syrk_sub(int64_t N, int K, const double* A, int64_t lda, double* C, int64_t ldc, double scale,
                    int32_t* tile_counter, void* stream);
 
+/* Y[N x S] = L[N x N] Z[S x N]^T for S <= 8 sample vectors, L lower triangular (only k <= row is read): the `root @
+ * base_samples` of MultivariateNormal.rsample when MaxPosteriorSampling draws a handful of joint samples
+ * (generation/sampling.py:89-155).  Memory-bound sweep over the triangle; any N, no alignment requirements.            */
+int mcacq_lower_times_few(int64_t N, int S, const double* L, int64_t ldl, const double* Z, int64_t ldz, double* Y, int64_t ldy,
+                          void* stream);
+
 /* ---- FP64-accurate contraction on the INT8 tensor cores (Ozaki-style splitting; csrc/ozaki_imma.cu) -------------
  * Optional replacement of mcacq_dgemm_tri for `test_train_covar @ covar_cache`:
  *   mcacq_slice_rows    : X[rows x K] (fp64) -> G signed 8-bit slices [G][rows][Kp] (balanced radix-256 digits) + row scale;

@@ -54,6 +54,13 @@ def test_joint_posterior_and_trmm_match_oracle():
     Z = torch.randn(64, N, device=dev, dtype=torch.float64)
     Y = strat.lower_times_samples(chol, Z)
     assert float((Y - chol @ Z.t()).abs().max() / Y.abs().max()) < 1e-12
+    # a handful of samples (S <= 8) takes the memory-bound row-sweep kernel; odd N needs no padding there
+    for S, Nn in ((4, N), (1, N - 1), (8, 7)):
+        Zs = torch.randn(S, Nn, device=dev, dtype=torch.float64)
+        Ls = chol[:Nn, :Nn].contiguous()
+        Ys = strat.lower_times_samples(Ls, Zs)
+        assert Ys.shape == (Nn, S)
+        assert float((Ys - Ls @ Zs.t()).abs().max() / Ys.abs().max()) < 1e-12
 
 
 @pytest.mark.gpu
