@@ -123,14 +123,53 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
+REFERENCE_KIND = "port"   # becomes "botorch" when a real BoTorch + gpytorch install is importable (never in this image)
+
+
+def _real_botorch_acqf(data, spec):
+    """The UNMODIFIED reference on the same synthetic problem, if `botorch` + `gpytorch` import (site-packages or
+    `baseline/_ref`); None otherwise.  (SURVEY.md fact 1 / VERDICT r01 item 1d: no wheels and no network here, so this
+    branch has never run in this image; `tests/test_real_botorch_probe.py` is its correctness twin.)"""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.append(ref)
+    try:
+        import gpytorch  # noqa: F401
+        from botorch.acquisition.logei import qLogExpectedImprovement, qLogNoisyExpectedImprovement
+        from botorch.models import SingleTaskGP
+        from botorch.models.transforms.outcome import Standardize
+        from botorch.sampling.normal import SobolQMCNormalSampler
+        from gpytorch.kernels import MaternKernel, RBFKernel, ScaleKernel
+    except Exception:  # noqa: BLE001 -- not installed / not importable: the oracle port is timed instead
+        return None
+    base = (RBFKernel if spec.kernel == "rbf" else MaternKernel)(ard_num_dims=spec.d)
+    base.lengthscale = data.lengthscale
+    covar = base
+    if spec.outputscale is not None:
+        covar = ScaleKernel(base)
+        covar.outputscale = spec.outputscale
+    model = SingleTaskGP(data.train_X, data.train_Y, covar_module=covar, outcome_transform=Standardize(m=1))
+    model.likelihood.noise = data.noise
+    model.mean_module.constant = 0.0
+    model.eval()
+    sampler = SobolQMCNormalSampler(sample_shape=torch.Size([spec.S]), seed=1234)
+    if spec.acqf == "qLogEI":
+        return qLogExpectedImprovement(model, best_f=data.best_f, sampler=sampler)
+    return qLogNoisyExpectedImprovement(model, X_baseline=data.X_baseline, sampler=sampler, prune_baseline=False)
+
+
 def cpu_reference(args, data, spec, steps, warmup, sample_b):
-    """The reference's CPU path (oracle port: pure-torch restatement, all host threads) on a bounded sample."""
+    """The reference's CPU path on a bounded sample, all host threads: real BoTorch when importable (kind "botorch"), else the
+    oracle port (pure-torch restatement, kind "port")."""
+    global REFERENCE_KIND
     from oracle.harness import build_oracle, time_cpu_fwd_bwd
     from botorch_b200.benchmarks import configs
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    orc = build_oracle(data)
+    real = _real_botorch_acqf(data, spec)
+    REFERENCE_KIND = "botorch" if real is not None else "port"
+    orc = real if real is not None else build_oracle(data)
     X = configs.eval_points(data, sample_b)
     chunk = min(sample_b, 64 if spec.n >= 4096 else 256)
     from oracle.acquisition import value_and_grad
@@ -170,7 +209,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "sample": sample},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": REFERENCE_KIND, "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -451,7 +490,7 @@ def main():
         if world == 1:
             sample_b = args.cpu_sample or (2048 if spec.n >= 4096 else 8192)  # ~10 s of host work (bounded sample)
             val, sec, threads, sample = cpu_reference(args, data, spec, 1, 1, sample_b)
-            cpu_base = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            cpu_base = {"value": val, "unit": UNIT, "cores": threads, "kind": REFERENCE_KIND, "sample": sample}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
