@@ -197,13 +197,17 @@ class SingleTaskGP(Model):
         batch_shape, q, d = X.shape[:-2], X.shape[-2], X.shape[-1]
         Xf = X.reshape(-1, q, d).to(device=strat.device, dtype=torch.float64)
         if q > _lib.MAX_Q:
-            # large joint posteriors (baseline sets, candidate sets, cat[X, X_baseline] of the generic qLogNEI route when
-            # r exceeds the fused kernels' limit): one point set at a time through the covariance / contraction kernels
-            if X.requires_grad and torch.is_grad_enabled():
-                ms, cs = zip(*(strat.joint_posterior_with_grad(x) for x in Xf))
+            # joint posteriors beyond the fused kernels' q limit (baseline sets, candidate sets, cat[X, X_baseline] of the generic
+            # qLogNEI route): through the covariance / contraction kernels
+            if Xf.shape[0] == 1 or q * q * d > (1 << 24):
+                # one (or a few) LARGE point sets: per set through the DMMA SYRK-sub kernel, no N x N x d intermediates
+                if X.requires_grad and torch.is_grad_enabled():
+                    ms, cs = zip(*(strat.joint_posterior_with_grad(x) for x in Xf))
+                else:
+                    ms, cs = zip(*(strat.joint_posterior(x) for x in Xf))
+                mean, covar = torch.stack(ms), torch.stack(cs)
             else:
-                ms, cs = zip(*(strat.joint_posterior(x) for x in Xf))
-            mean, covar = torch.stack(ms), torch.stack(cs)
+                mean, covar = strat.batched_joint_posterior(Xf)   # all t-batches in one pass (no Python loop over b)
         else:
             mean, covar = self._posterior_chunks(Xf, strat)
         if isinstance(observation_noise, Tensor) or observation_noise:

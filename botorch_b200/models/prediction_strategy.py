@@ -10,6 +10,7 @@ triangular solve (a plain library call on an n x n matrix, off the per-evaluatio
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import warnings
 
@@ -407,6 +408,16 @@ class DevicePredictionStrategy:
         mean = self.y_mean + self.y_std * (self.mean_const + Kt @ self.alpha)
         return mean, Kxx
 
+    def batched_joint_posterior(self, X: Tensor, max_rows: int = 1 << 16) -> tuple[Tensor, Tensor]:
+        """Differentiable joint posteriors of B point sets at once: X [B x N x d] -> mean [B x N], covar [B x N x N]
+        (`_BatchedJointPosterior`), chunked so that one pass holds at most ~`max_rows` rows of the contraction."""
+        B, N, d = X.shape
+        step = max(1, min(max_rows // max(N, 1), (1 << 27) // max(N * N * d, 1)))   # rows of A, and the N x N x d differences
+        if B <= step:
+            return _BatchedJointPosterior.apply(X, self)
+        ms, cs = zip(*(_BatchedJointPosterior.apply(X[i:i + step], self) for i in range(0, B, step)))
+        return torch.cat(ms), torch.cat(cs)
+
     def joint_posterior_with_grad(self, X: Tensor) -> tuple[Tensor, Tensor]:
         """Differentiable `joint_posterior` (N x d -> mean [N], covar [N x N]) for joint posteriors beyond the fused kernels'
         q limit, e.g. the generic qLogNEI route over cat[X, X_baseline] when r > MCACQ_MAX_R."""
@@ -430,6 +441,85 @@ class DevicePredictionStrategy:
         _lib.check(_lib.lib().mcacq_dgemm_nt(1, N, S, N, chol.data_ptr(), N, Z.data_ptr(), N, Y.data_ptr(), S,
                                              counter.data_ptr(), _lib.stream_ptr()), "dgemm_nt (trmm)")
         return Y
+
+
+def _self_kernel_blocks(U3: Tensor, kernel_id: int, outputscale: float) -> Tensor:
+    """k(u_i, u_j) inside every t-batch of scaled points U3 [B x N x d] -> [B x N x N], from direct differences (like the CUDA
+    covariance kernels: no GEMM-expansion cancellation); differentiable torch ops, Matern gradient zero at coincident points
+    (the reference's `clamp_min(1e-30).sqrt()`)."""
+    diff = U3.unsqueeze(-2) - U3.unsqueeze(-3)
+    sq = diff.square().sum(dim=-1)
+    if kernel_id == 0:
+        return outputscale * torch.exp(-0.5 * sq)
+    r = sq.clamp_min(1e-30).sqrt()
+    s5r = math.sqrt(5.0) * r
+    return outputscale * (1.0 + s5r + (5.0 / 3.0) * sq) * torch.exp(-s5r)
+
+
+class _BatchedJointPosterior(torch.autograd.Function):
+    """Joint posteriors of B point sets of N points each in ONE pass: X [B x N x d] -> mean [B x N], covar [B x N x N].
+
+    The route of everything the fused kernels do not cover (N = q + r > 32 points per t-batch: generic qLogNEI with a custom
+    objective or a baseline beyond 64 points, `model.posterior` on large q): the cross-covariance against the training set
+    and the contraction `A = K R` run ONCE over all B N rows in the hand-written kernels, the per-set Grams `A_b A_b^T` are one
+    batched library matmul, the small within-set kernel blocks are torch ops.  Backward: dA = -s^2 (G + G^T) A per set (bmm),
+    dKt = dA R^T (DMMA kernel), dU from `mcacq_cov_cross_bwd` with the rank-1 mean term, plus autograd through the
+    within-set blocks.  (Round 1 looped over the t-batch in Python: ~8 launches per q-batch.)"""
+
+    @staticmethod
+    def forward(ctx, X: Tensor, strat: "DevicePredictionStrategy"):
+        B, N, d = X.shape
+        Xc = X.detach().to(device=strat.device, dtype=torch.float64).reshape(-1, d).contiguous()
+        M = Xc.shape[0]
+        L, st = _lib.lib(), _lib.stream_ptr()
+        f64 = dict(device=strat.device, dtype=torch.float64)
+        U = strat.scale(Xc)
+        Kt = torch.empty(M, strat.np, **f64)
+        _lib.check(L.mcacq_cov_cross(strat.kernel_id, strat.outputscale, U.data_ptr(), M, strat.U_train.data_ptr(), strat.n,
+                                     strat.d, Kt.data_ptr(), strat.np, st), "cov_cross")
+        A = torch.empty(M, strat.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=strat.device)
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, M, strat.np, Kt.data_ptr(), strat.R.data_ptr(), A.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        mean = (strat.y_mean + strat.y_std * (strat.mean_const + Kt @ strat.alpha)).view(B, N)
+        del Kt
+        A3 = A.view(B, N, strat.np)
+        Kxx = _self_kernel_blocks(U.view(B, N, d), strat.kernel_id, strat.outputscale)
+        covar = (strat.y_std**2) * (Kxx - torch.bmm(A3, A3.mT))
+        ctx.strat = strat
+        ctx.save_for_backward(U, A)
+        ctx.dims = (B, N, d)
+        return mean, covar
+
+    @staticmethod
+    def backward(ctx, gmean: Tensor, gcovar: Tensor):
+        U, A = ctx.saved_tensors
+        strat = ctx.strat
+        B, N, d = ctx.dims
+        M = B * N
+        L, st = _lib.lib(), _lib.stream_ptr()
+        f64 = dict(device=strat.device, dtype=torch.float64)
+        gm = torch.zeros(M, **f64) if gmean is None else gmean.to(**f64).reshape(M).contiguous()
+        gc = torch.zeros(B, N, N, **f64) if gcovar is None else gcovar.to(**f64)
+        s2 = strat.y_std**2
+        dA = (-s2 * torch.bmm(gc + gc.mT, A.view(B, N, strat.np))).reshape(M, strat.np).contiguous()
+        dKt = torch.empty(M, strat.np, **f64)
+        counter = torch.zeros(64, dtype=torch.int32, device=strat.device)
+        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_LOWER, M, strat.np, dA.data_ptr(), strat.Rt.data_ptr(), dKt.data_ptr(),
+                                     counter.data_ptr(), st), "dgemm_tri")
+        del dA
+        rs = (strat.y_std * gm).contiguous()
+        dU = torch.empty(M, strat.d, **f64)
+        _lib.check(L.mcacq_cov_cross_bwd(strat.kernel_id, strat.outputscale, U.data_ptr(), M, strat.U_train.data_ptr(), strat.n,
+                                         strat.d, dKt.data_ptr(), strat.np, rs.data_ptr(), strat.alpha.data_ptr(),
+                                         dU.data_ptr(), 0, st), "cov_cross_bwd(train)")
+        del dKt
+        with torch.enable_grad():
+            U3 = U.view(B, N, d).detach().requires_grad_(True)
+            Kxx = _self_kernel_blocks(U3, strat.kernel_id, strat.outputscale)
+            (gU,) = torch.autograd.grad(Kxx, U3, grad_outputs=s2 * gc)
+        dU = dU + gU.reshape(M, d)
+        return (dU / (strat.x_coef * strat.lengthscale)).view(B, N, d), None
 
 
 class _JointPosterior(torch.autograd.Function):
