@@ -165,37 +165,61 @@ def run_c4(args, ClockSampler, impl_reference=False):
     line = None
     if rank == 0:
         # phases of one trust region, each timed alone with CUDA events on the launching stream
+        from botorch_b200 import settings
+
         L = _lib.lib()
         st = _lib.stream_ptr()
         f64 = dict(device=dev, dtype=torch.float64)
         xb = X_dev[0]
-        U = strat.scale(xb)
-        Kt, A = torch.empty(N, strat.np, **f64), torch.empty(N, strat.np, **f64)
-        Kxx, G = torch.empty(N, N, **f64), torch.zeros(N, N, **f64)
-        counter = torch.zeros(64, dtype=torch.int32, device=dev)
         ph = {}
-        ph["cov_cross (N x n and N x N)"] = _event_ms(lambda: (
-            L.mcacq_cov_cross(strat.kernel_id, strat.outputscale, U.data_ptr(), N, strat.U_train.data_ptr(), strat.n, strat.d, Kt.data_ptr(), strat.np, st),
-            L.mcacq_cov_cross(strat.kernel_id, strat.outputscale, U.data_ptr(), N, U.data_ptr(), N, strat.d, Kxx.data_ptr(), N, st)))
-        ph["dgemm_tri  A = K R"] = _event_ms(lambda: L.mcacq_dgemm_tri(_lib.TRI_UPPER, N, strat.np, Kt.data_ptr(), strat.R.data_ptr(), A.data_ptr(), counter.data_ptr(), st))
-        ph["dgemm_nt   A A^T (SYRK)"] = _event_ms(lambda: L.mcacq_syrk_sub(N, strat.np, A.data_ptr(), strat.np, G.data_ptr(), N, strat.y_std**2, counter.data_ptr(), st))
+        ph["joint posterior, as MaxPosteriorSampling runs it (mode %s)" % strat.contraction] = _event_ms(lambda: strat.joint_posterior(xb))
+        with settings.int8_gram(False):
+            ph["joint posterior with the Gram on the FP64 DMMA SYRK-sub kernel"] = _event_ms(lambda: strat.joint_posterior(xb))
         mean, covar = strat.joint_posterior(xb)
         ph["cholesky N x N (cuSOLVER potrf, library)"] = _event_ms(lambda: psd_safe_cholesky(covar, max_tries=6))
         chol = psd_safe_cholesky(covar, max_tries=6)
         Z = torch.randn(ns, N, **f64)
         ph["L z (lower_times_few, memory-bound row sweep)"] = _event_ms(lambda: strat.lower_times_samples(chol, Z))
         fp64_peak = _dgemm_peak(dev)
-        syrk_flops = float(N) * (N + 1) * strat.np    # 2 flop per k over the N (N + 1) / 2 entries on and below the diagonal
-        syrk_ms = ph["dgemm_nt   A A^T (SYRK)"]
-        ach = syrk_flops / (syrk_ms * 1e-3) * 1e-12
         alg_tr = float(N) * strat.np * (strat.np + 1) + float(N) * (N + 1) * strat.np + float(N) ** 3 / 3.0
-        roofline = {"bound": "tensor", "kernel": "dgemm_nt_kernel mode 2 (FP64 DMMA.8x8x4): covar = s^2 (K - A A^T), symmetric", "achieved": ach,
-                    "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None, "launch_ms": syrk_ms,
-                    "alg_flops_per_launch": syrk_flops,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    "note": "algorithmic flops = N (N + 1) n: only tiles on and below the diagonal are contracted, results are mirrored",
-                    "step_alg_tflops": alg_tr * T / (ms / args.steps * 1e-3) * 1e-12,
-                    "alg_flops_per_trust_region": alg_tr}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        if strat.contraction == "int8":
+            # dominant own kernel: the Gram A A^T on the INT8 tensor cores (dense N x N x np, G (G + 1) / 2 slice products)
+            v = strat.max_slices_view()
+            G = int(v.g_fwd)
+            A = torch.rand(N, strat.np, **f64)
+            As, a_scale = strat._slice_rows(A, G)
+            Gm = torch.empty(N, N, **f64)
+            gram_ms = _event_ms(lambda: L.mcacq_ozaki_contract(_lib.TRI_DENSE, N, N, strat.np, G, As.data_ptr(), a_scale.data_ptr(),
+                                                               As.data_ptr(), a_scale.data_ptr(), Gm.data_ptr(), N, st))
+            pairs = G * (G + 1) // 2
+            flops = 2.0 * N * N * strat.np                      # executed: the full square
+            ach = flops / (gram_ms * 1e-3) * 1e-12
+            peak_equiv = 2.0 * bf16_peak / pairs
+            roofline = {"bound": "tensor", "kernel": f"ozaki_imma_kernel (tcgen05 kind::i8, G={G}, dense): Gram A A^T of the joint covariance",
+                        "achieved": ach, "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": None,
+                        "launch_ms": gram_ms, "alg_flops_per_launch": flops, "int8_tops": ach * pairs,
+                        "peak_source": f"2 x bf16_tflops (MEASURED_PEAKS.json or the 1.59 PF fallback) / {pairs} int8 slice products per fp64 multiply-add",
+                        "fp64_dgemm_peak_measured": fp64_peak,
+                        "note": "fp64-equivalent rate of the executed (full-square) Gram; the symmetric half on the DMMA pipe (SYRK-sub) takes 1.85 ms",
+                        "step_alg_tflops": alg_tr * T / (ms / args.steps * 1e-3) * 1e-12, "alg_flops_per_trust_region": alg_tr}
+        else:
+            A = torch.rand(N, strat.np, **f64)
+            Gm = torch.zeros(N, N, **f64)
+            counter = torch.zeros(64, dtype=torch.int32, device=dev)
+            syrk_ms = _event_ms(lambda: L.mcacq_syrk_sub(N, strat.np, A.data_ptr(), strat.np, Gm.data_ptr(), N, strat.y_std**2, counter.data_ptr(), st))
+            syrk_flops = float(N) * (N + 1) * strat.np
+            ach = syrk_flops / (syrk_ms * 1e-3) * 1e-12
+            roofline = {"bound": "tensor", "kernel": "dgemm_nt_kernel mode 2 (FP64 DMMA.8x8x4): covar = s^2 (K - A A^T), symmetric", "achieved": ach,
+                        "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None, "launch_ms": syrk_ms,
+                        "alg_flops_per_launch": syrk_flops,
+                        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                        "step_alg_tflops": alg_tr * T / (ms / args.steps * 1e-3) * 1e-12, "alg_flops_per_trust_region": alg_tr}
         cpu = None
         if world == 1:
             val, sec, threads, sample = _c4_cpu(data, N, ns, 1)
@@ -207,7 +231,7 @@ def run_c4(args, ClockSampler, impl_reference=False):
                            "parallelism": f"{T} independent trust regions per GPU, {world} GPU(s), no data-path collective"},
                 "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": T * world * N * d * 8, "d2h_bytes_per_step": T * world * ns * d * 8,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": 5 * T * args.steps, "clocks": clock_info, "roofline": roofline,
+                "gpu_launches": 8 * T * args.steps, "clocks": clock_info, "roofline": roofline,
                 "phases_ms_per_trust_region": ph}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -392,20 +392,50 @@ class DevicePredictionStrategy:
         st = _lib.stream_ptr()
         U = self.scale(X)
         f64 = dict(device=self.device, dtype=torch.float64)
-        Kt = torch.empty(N, self.np, **f64)
-        _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, self.U_train.data_ptr(),
-                                     self.n, self.d, Kt.data_ptr(), self.np, st), "cov_cross")
         A = torch.empty(N, self.np, **f64)
         counter = torch.zeros(64, dtype=torch.int32, device=self.device)
-        _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, N, self.np, Kt.data_ptr(), self.R.data_ptr(), A.data_ptr(),
-                                     counter.data_ptr(), st), "dgemm_tri")
+        if self.contraction == "int8":
+            # the contraction on the INT8 tensor cores with the most accurate slice counts (FP64-level: 2^-54 of the prior): the
+            # covariance kernel emits the slices and the partial sums of K alpha directly (as in the fused forward pass)
+            v = self.max_slices_view()
+            G = v.g_fwd
+            _, e = math.frexp(self.outputscale)
+            n_tiles = (self.np + 63) // 64
+            n_parts = (n_tiles + 7) // 8
+            slices = torch.empty(G, N, self.np, dtype=torch.int8, device=self.device)
+            mean_part = torch.empty(n_tiles * N, **f64)
+            _lib.check(L.mcacq_cov_cross_sliced(self.kernel_id, self.outputscale, U.data_ptr(), N, self.U_train.data_ptr(), self.n,
+                                                self.d, self.np, self.alpha.data_ptr(), G, e, slices.data_ptr(),
+                                                mean_part.data_ptr(), st), "cov_cross_sliced")
+            scale = torch.full((N,), 2.0 ** (e + 2), **f64)
+            _lib.check(L.mcacq_ozaki_contract(_lib.TRI_UPPER, N, self.np, self.np, G, slices.data_ptr(), scale.data_ptr(),
+                                              v.Rt_slices.data_ptr(), v.Rt_scale.data_ptr(), A.data_ptr(), self.np, st),
+                       "ozaki_contract")
+            k_alpha = mean_part[: n_parts * N].view(n_parts, N).sum(dim=0)
+        else:
+            Kt = torch.empty(N, self.np, **f64)
+            _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, self.U_train.data_ptr(),
+                                         self.n, self.d, Kt.data_ptr(), self.np, st), "cov_cross")
+            _lib.check(L.mcacq_dgemm_tri(_lib.TRI_UPPER, N, self.np, Kt.data_ptr(), self.R.data_ptr(), A.data_ptr(),
+                                         counter.data_ptr(), st), "dgemm_tri")
+            k_alpha = Kt @ self.alpha
         Kxx = torch.empty(N, N, **f64)
         _lib.check(L.mcacq_cov_cross(self.kernel_id, self.outputscale, U.data_ptr(), N, U.data_ptr(), N, self.d,
                                      Kxx.data_ptr(), N, st), "cov_cross")
-        # covar = s^2 (K(X, X) - A A^T) in place: lower tiles only, mirrored stores (csrc/dgemm_nt.cu, mode 2)
-        _lib.check(L.mcacq_syrk_sub(N, self.np, A.data_ptr(), self.np, Kxx.data_ptr(), N, self.y_std**2, counter.data_ptr(), st),
-                   "syrk_sub")
-        mean = self.y_mean + self.y_std * (self.mean_const + Kt @ self.alpha)
+        if self.contraction == "int8" and N >= 1024 and settings.int8_gram.value():
+            # large candidate sets: the Gram A A^T on the INT8 tensor cores as well (slices of A against themselves, dense mode;
+            # the full square at ~100 TF/s fp64-equivalent beats the symmetric half on the 35 TF/s DMMA pipe)
+            As, a_scale = self._slice_rows(A, G)
+            Gm = torch.empty(N, N, **f64)
+            _lib.check(L.mcacq_ozaki_contract(_lib.TRI_DENSE, N, N, self.np, G, As.data_ptr(), a_scale.data_ptr(), As.data_ptr(),
+                                              a_scale.data_ptr(), Gm.data_ptr(), N, st), "ozaki_contract (gram)")
+            del As
+            Kxx.sub_(Gm).mul_(self.y_std**2)   # (the int8 Gram is EXACTLY symmetric: integer slice products, commutative scales)
+        else:
+            # covar = s^2 (K(X, X) - A A^T) in place: lower tiles only, mirrored stores (csrc/dgemm_nt.cu, mode 2)
+            _lib.check(L.mcacq_syrk_sub(N, self.np, A.data_ptr(), self.np, Kxx.data_ptr(), N, self.y_std**2, counter.data_ptr(), st),
+                       "syrk_sub")
+        mean = self.y_mean + self.y_std * (self.mean_const + k_alpha)
         return mean, Kxx
 
     def batched_joint_posterior(self, X: Tensor, max_rows: int = 1 << 16) -> tuple[Tensor, Tensor]:

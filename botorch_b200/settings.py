@@ -55,5 +55,6 @@ contraction = _Flag("int8")
 int8_slices = _Flag(None)
 int8_cond_limit = _Flag("auto")
 int8_max_slices = _Flag(False)
+int8_gram = _Flag(True)       # joint posteriors over >= 1024 points: Gram A A^T on the INT8 tensor cores (False: DMMA SYRK)
 fused_log_hvi = _Flag(True)   # qLogEHVI: one fused kernel for the inclusion-exclusion loop (False: per-subset-size kernels)
 optimizer = _Flag("scipy")

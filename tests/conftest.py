@@ -54,3 +54,4 @@ def _restore_settings():
     settings.int8_cond_limit.set(saved[2])
     settings.int8_max_slices.set(False)
     settings.fused_log_hvi.set(True)
+    settings.int8_gram.set(True)

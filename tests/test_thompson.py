@@ -112,6 +112,12 @@ def test_joint_posterior_at_config4_size_matches_oracle_on_row_slices():
     Xc = (center + 0.4 * (torch.rand(N, 20, generator=g, dtype=torch.float64) - 0.5)).clamp(0.0, 1.0)
     mean, covar = strat.joint_posterior(Xc.to(dev))
     assert mean.shape == (N,) and covar.shape == (N, N)
+    assert torch.equal(covar, covar.mT)      # exactly symmetric on both Gram routes (int8 slices / mirrored DMMA tiles)
+    from botorch_b200 import settings
+
+    with settings.int8_gram(False):          # DMMA SYRK-sub route for the Gram: same covariance to 1e-12 of its scale
+        _, covar_dmma = strat.joint_posterior(Xc.to(dev))
+    assert float((covar - covar_dmma).abs().max() / covar_dmma.abs().max()) < 1e-12
     gp = build_oracle(data).gp
     var = covar.diagonal().cpu()
     slices = [torch.arange(0, 96), torch.arange(N - 96, N), var.argsort()[:96], torch.randperm(N, generator=g)[:96]]
