@@ -22,7 +22,7 @@ TRI_UPPER, TRI_LOWER, TRI_DENSE = 0, 1, 2
 INFO_JITTER_MASK, INFO_NOT_PSD, INFO_NONFINITE = 0x7, 0x8, 0x10
 INFO_FLAG_MASK, INFO_COND_SHIFT, INFO_COND_MASK = 0x1F, 8, 0xFF00
 INFO_VAR_SHIFT, INFO_VAR_MASK = 16, 0xFF0000
-MAX_Q, MAX_D, MAX_R = 32, 64, 64
+MAX_Q, MAX_D, MAX_R = 32, 64, 512
 
 _ERRORS = {-1: "MCACQ_EINVAL (bad argument)", -2: "MCACQ_ELIMIT (q/r/d/S outside compiled limits)",
            -3: "MCACQ_EWORKSPACE (workspace too small)"}
@@ -75,6 +75,7 @@ EXPORTS = [
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_log_hvi_forward", "mcacq_log_hvi_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_lower_times_few", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
     "mcacq_sample_reduce_forward", "mcacq_info_summary", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
+    "mcacq_fused_supported",
 ]
 
 
@@ -129,6 +130,12 @@ def lib() -> C.CDLL:
             fn.restype = i32
     _lib = L
     return L
+
+
+def fused_supported(q: int, r: int, S: int, mc_mean: bool = False) -> bool:
+    """Whether `mcacq_acq_forward / _backward` take this shape (compiled limits + the shared memory of the sample / reduce
+    kernels, which grows with q * r); host-only query."""
+    return bool(lib().mcacq_fused_supported(int(q), int(r), int(S), int(bool(mc_mean))))
 
 
 def check(rc: int, what: str) -> None:

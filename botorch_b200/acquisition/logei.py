@@ -270,7 +270,8 @@ class qLogNoisyExpectedImprovement(LogImprovementMCAcquisitionFunction, CachedCh
     @t_batch_mode_transform()
     def forward(self, X: Tensor) -> Tensor:
         fused = (self._fusable(X) and self._cache_root and hasattr(self, "_baseline_L")
-                 and self.X_baseline.dim() == 2 and self.X_baseline.shape[-2] <= _lib.MAX_R)
+                 and self.X_baseline.dim() == 2
+                 and _lib.fused_supported(X.shape[-2], self.X_baseline.shape[-2], self.sample_shape.numel()))
         if not fused:
             return self._sample_reduction(self._q_reduction(self._non_reduced_forward(X=X)))
         strat = self.model.prediction_strategy()

@@ -35,6 +35,8 @@ int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st);
 int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 int info_summary(const int32_t* info, int64_t b, int32_t* out, cudaStream_t st);
+size_t sample_reduce_fwd_smem(int q, int r, int S);
+size_t sample_reduce_bwd_smem(int q, int r, int S, bool mc_mean);
 
 struct Workspace {
   double *U, *Kt, *A, *mean, *Sxx, *Sxb, *Bm, *Cm, *gmean, *gSxx, *gSxb, *row_scale, *dU, *slice_scale, *mean_part,
@@ -260,6 +262,12 @@ static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc
   sp.Bm = w.Bm; sp.Cm = w.Cm;
   sp.acq = nullptr; sp.info = nullptr; sp.grad_acq = nullptr;
   sp.gmean = w.gmean; sp.gSxx = w.gSxx; sp.gSxb = w.gSxb;
+}
+
+extern "C" int mcacq_fused_supported(int q, int r, int S, int mc_mean) {
+  if (q <= 0 || q > MCACQ_MAX_Q || r < 0 || r > MCACQ_MAX_R || S <= 0) return 0;
+  const size_t limit = 200 * 1024;   // what the sample / reduce launchers accept
+  return sample_reduce_fwd_smem(q, r, S) <= limit && sample_reduce_bwd_smem(q, r, S, mc_mean != 0) <= limit;
 }
 
 extern "C" int mcacq_acq_forward(const mcacq_model* model, const mcacq_baseline* base, const mcacq_mc* mc,

@@ -18,7 +18,30 @@ namespace mcacq {
 int posterior_blocks_fwd_q2(const BlocksParams& p, cudaStream_t st);
 int posterior_blocks_fwd_q4(const BlocksParams& p, cudaStream_t st);
 
-int posterior_blocks_fwd(const BlocksParams& p, cudaStream_t st) {
+static int posterior_blocks_fwd_chunk(const BlocksParams& p, cudaStream_t st);
+
+// Baselines beyond 64 points: the accumulators of the cross-Gram live in registers (8 row tiles at most), so the baseline is
+// swept in chunks of 64 rows, one launch per chunk.  The first launch also produces mean / Sxx / the row maxima; the others
+// only write their columns of Sxb.  Every Sxb entry is the same DMMA sequence over k as in a single-chunk launch.
+int posterior_blocks_fwd(const BlocksParams& p0, cudaStream_t st) {
+  BlocksParams p = p0;
+  p.r_pitch = p0.r;
+  p.cross_only = 0;
+  if (p0.r <= 64) return posterior_blocks_fwd_chunk(p, st);
+  for (int r0 = 0; r0 < p0.r; r0 += 64) {
+    p.r = (p0.r - r0 < 64) ? p0.r - r0 : 64;
+    p.A_base = p0.A_base + (int64_t)r0 * p0.np;
+    p.U_base = p0.U_base + (int64_t)r0 * p0.d;
+    p.Sxb = p0.Sxb + r0;
+    p.cross_only = r0 > 0;
+    if (r0 > 0) { p.Kt = nullptr; p.A_absmax = nullptr; }   // (mean and row maxima come from the first launch)
+    const int rc = posterior_blocks_fwd_chunk(p, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int posterior_blocks_fwd_chunk(const BlocksParams& p, cudaStream_t st) {
   const int qt_ = (p.q + 7) / 8, rt_ = (p.r + 7) / 8;
   if (qt_ == 1) {
     if (rt_ == 0) return launch_blocks_fwd<1, 0>(p, st);

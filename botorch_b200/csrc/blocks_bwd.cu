@@ -15,7 +15,12 @@ namespace mcacq {
 // ACTUAL row maximum matters: the a-priori bound sum_j |C[i][j]| max|A[j][:]| (PASS = 0, kept behind MCACQ_DA_BOUND=1)
 // overestimates rows whose terms cancel -- nearly collinear rows of A with alternating coefficients, i.e. exactly the
 // ill-conditioned q-batches -- by the inverse of the smallest relative pivot, and every factor 256 costs one slice.
-template <int QT, int RT, int PASS>
+//
+// RLOOP (baselines of more than 64 points; instantiated with RT = 0): the baseline coefficients and source rows do not fit
+// the register file, so the baseline term is accumulated by a run-time loop over groups of 4 baseline rows whose
+// coefficient fragments are re-read (L1 / L2) in every column step -- the same DMMA sequence, in the same order, as the
+// unrolled RT version.
+template <int QT, int RT, int PASS, bool RLOOP = false>
 __global__ void __launch_bounds__(BLK_WARPS * 32, (QT == 1 && RT <= 2) ? 4 : 1)
 posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -80,6 +85,11 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
         const int j = kk * 4 + t4;
         if (j < r) bnd = fma(fabs(cb[mi][kk]), p.Ab_absmax[j], bnd);
       }
+      if (RLOOP) {
+        const int i = mi * 8 + g;
+        for (int j = t4; j < r; j += 4)
+          if (i < q) bnd = fma(fabs(s2 * gxb[i * r + j]), p.Ab_absmax[j], bnd);
+      }
       bnd += __shfl_xor_sync(0xffffffffu, bnd, 1);
       bnd += __shfl_xor_sync(0xffffffffu, bnd, 2);
       int ex = 0;
@@ -120,6 +130,24 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
 #pragma unroll
         for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cb[mi][kk], rb[kk][t]);
       loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < r && cn < col_end, rb[kk]);
+    }
+    if (RLOOP) {
+      const int cc = c0 + NT * g;   // this lane's source columns in the current step
+#pragma unroll 4
+      for (int j0 = 0; j0 < r; j0 += 4) {
+        const int j = j0 + t4;
+        double rbj[NT], cbj[QT];
+        loadn<NT>(p.A_base + (int64_t)j * np + cc, j < r && cc < col_end, rbj);
+#pragma unroll
+        for (int mi = 0; mi < QT; mi++) {
+          const int i = mi * 8 + g;
+          cbj[mi] = (i < q && j < r) ? -s2 * gxb[i * r + j] : 0.0;
+        }
+#pragma unroll
+        for (int mi = 0; mi < QT; mi++)
+#pragma unroll
+          for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cbj[mi], rbj[t]);
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < 2 * QT; kk++) {
@@ -222,7 +250,7 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
   }
 }
 
-template <int QT, int RT>
+template <int QT, int RT, bool RLOOP = false>
 static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
   // the output columns are independent, so the chunk width is free to follow the batch size: one warp per q-batch when
   // there are thousands of them (no duplicated preamble), narrow chunks when an L-BFGS round brings only a few dozen
@@ -238,18 +266,31 @@ static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
     // 0x80808080 = -2139062144: below every frexp exponent
     if (cudaMemsetAsync(p.slice_exp, 0x80, (size_t)p.b * p.q * sizeof(int32_t), st) != cudaSuccess)
       return (int)cudaGetLastError();
-    posterior_blocks_bwd_kernel<QT, RT, 1><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+    posterior_blocks_bwd_kernel<QT, RT, 1, RLOOP><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
     count_launch();
     MCACQ_CUDA_CHECK_LAUNCH();
-    posterior_blocks_bwd_kernel<QT, RT, 2><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+    posterior_blocks_bwd_kernel<QT, RT, 2, RLOOP><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
   } else {
-    posterior_blocks_bwd_kernel<QT, RT, 0><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
+    posterior_blocks_bwd_kernel<QT, RT, 0, RLOOP><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
   }
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
-int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) { MCACQ_DISPATCH_QT_RT(launch_blocks_bwd, p, st); }
+static int posterior_blocks_bwd_small_r(const BlocksBwdParams& p, cudaStream_t st) {
+  MCACQ_DISPATCH_QT_RT(launch_blocks_bwd, p, st);
+}
+
+int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
+  // MCACQ_BWD_RLOOP=1 forces the run-time baseline loop for every r (tests: bit-identical to the unrolled kernels)
+  const bool force_rloop = (getenv("MCACQ_BWD_RLOOP") != nullptr) && atoi(getenv("MCACQ_BWD_RLOOP")) != 0;
+  if (p.r <= 64 && !(force_rloop && p.r > 0)) return posterior_blocks_bwd_small_r(p, st);
+  const int qt_ = (p.q + 7) / 8;
+  if (qt_ == 1) return launch_blocks_bwd<1, 0, true>(p, st);
+  if (qt_ == 2) return launch_blocks_bwd<2, 0, true>(p, st);
+  if (qt_ <= 4) return launch_blocks_bwd<4, 0, true>(p, st);
+  return MCACQ_ELIMIT;
+}
 
 }  // namespace mcacq

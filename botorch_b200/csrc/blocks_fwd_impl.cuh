@@ -175,7 +175,7 @@ posterior_blocks_kernel(BlocksParams p) {
       av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 1));
       av = fmax(av, __shfl_xor_sync(0xffffffffu, av, 2));
       const int i = mi * 8 + g;
-      if (t4 == 0 && i < q) {
+      if (t4 == 0 && i < q && !p.cross_only) {
         if (p.mean_part != nullptr) {  // int8 mode: Kt * alpha was reduced per 512-column tile by the covariance kernel
           const int64_t Mrows = p.b * q;
           mv = 0.0;
@@ -190,7 +190,7 @@ posterior_blocks_kernel(BlocksParams p) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int j = nj * 8 + 2 * t4 + e;
-          if (j >= q) continue;
+          if (j >= q || p.cross_only) continue;
           double sq = 0.0;
           for (int k = 0; k < p.d; k++) {
             double df = Ub[i * p.d + k] - Ub[j * p.d + k];
@@ -211,7 +211,7 @@ posterior_blocks_kernel(BlocksParams p) {
             double df = Ub[i * p.d + k] - p.U_base[j * p.d + k];
             sq = fma(df, df, sq);
           }
-          p.Sxb[(bb * q + i) * r + j] = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - B_[mi][nj][e]);
+          p.Sxb[(bb * q + i) * (int64_t)p.r_pitch + j] = s2 * (kernel_value(p.kernel_id, p.outputscale, sq) - B_[mi][nj][e]);
         }
     }
   }

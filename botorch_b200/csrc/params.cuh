@@ -18,7 +18,11 @@ struct BlocksParams {
   const double* U_base; // [r x d]
   double* mean;         // [b*q]
   double* Sxx;          // [b x q x q]
-  double* Sxb;          // [b x q x r]
+  double* Sxb;          // [b x q x r_pitch]
+  // baselines of more than 64 points are swept in chunks of 64 rows (one launch each): `r` is the chunk's row count, A_base /
+  // U_base / Sxb point at the chunk's first row / column, `r_pitch` is the row pitch of Sxb (the whole baseline) and chunks
+  // after the first only write their Sxb columns (`cross_only`)
+  int r_pitch, cross_only;
 };
 
 struct BlocksBwdParams {

@@ -301,6 +301,9 @@ static size_t fwd_smem(int q, int r, int S, int wide) {
   return ((size_t)(r + q) * QP + scratch + (size_t)q * q + q + 2 * SR_WARPS + q + (wide ? (size_t)S : 0)) * sizeof(double);
 }
 
+// dynamic shared memory of the (wide, i.e. larger) forward launch for this shape (host-side query: mcacq_fused_supported)
+size_t sample_reduce_fwd_smem(int q, int r, int S) { return fwd_smem(q, r, S, 1); }
+
 template <int QMAX, int NS, int W, bool PLAIN = false>
 static int launch_sr_fwd(const SRParams& p, cudaStream_t st) {
   size_t smem = fwd_smem(p.q, p.r, p.S, W > 1);

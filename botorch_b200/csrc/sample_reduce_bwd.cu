@@ -283,15 +283,26 @@ static size_t bwd_smem(int q, int r, int chunk, int qmax, bool mc_mean) {
           (size_t)SR_WARPS * qmax * 8 + 2 * (size_t)q + (mc_mean ? (size_t)(chunk + 4) * GP : 0)) * sizeof(double);
 }
 
+static int bwd_chunk(int q, int r, int S, int ns, bool mc_mean) {
+  int chunk = ((mc_mean ? 18 : 36) * 1024) / (8 * (q | 1));
+  if (chunk > S) chunk = S;
+  chunk = (chunk / (SR_THREADS * ns)) * (SR_THREADS * ns);
+  if (chunk < SR_THREADS * ns) chunk = SR_THREADS * ns;
+  if ((int64_t)chunk * (q | 1) < (int64_t)q * r) chunk = (q * r + (q | 1) - 1) / (q | 1);
+  return chunk;
+}
+
+// dynamic shared memory of the backward launch for this shape (host-side query: mcacq_fused_supported)
+size_t sample_reduce_bwd_smem(int q, int r, int S, bool mc_mean) {
+  const int qmax = q <= 8 ? 8 : q <= 16 ? 16 : 32;
+  return bwd_smem(q, r, bwd_chunk(q, r, S, 1, mc_mean), qmax, mc_mean);
+}
+
 template <int QMAX, int NS, int W, bool PLAIN = false>
 static int launch_sr_bwd(const SRParams& p, cudaStream_t st) {
   // chunk of samples whose weights are staged in shared memory (<= ~64 KB), at least r rows for the solve scratch
   const bool mc_mean = p.fat >= 5;
-  int chunk = ((mc_mean ? 18 : 36) * 1024) / (8 * (p.q | 1));
-  if (chunk > p.S) chunk = p.S;
-  chunk = (chunk / (SR_THREADS * NS)) * (SR_THREADS * NS);
-  if (chunk < SR_THREADS * NS) chunk = SR_THREADS * NS;
-  if ((int64_t)chunk * (p.q | 1) < (int64_t)p.q * p.r) chunk = (p.q * p.r + (p.q | 1) - 1) / (p.q | 1);
+  const int chunk = bwd_chunk(p.q, p.r, p.S, NS, mc_mean);
   size_t smem = bwd_smem(p.q, p.r, chunk, QMAX, mc_mean);
   if (smem > 200 * 1024) return MCACQ_ELIMIT;
   auto kern = sample_reduce_bwd_kernel<QMAX, NS, W, PLAIN>;

@@ -183,7 +183,8 @@ def _fused_capable(acqf, X: Tensor) -> bool:
             and getattr(acqf, "X_pending", None) is None
             and (not hasattr(acqf, "_baseline_operands")
                  or (getattr(acqf, "_cache_root", False) and hasattr(acqf, "_baseline_L")
-                     and acqf.X_baseline.dim() == 2 and acqf.X_baseline.shape[-2] <= _lib.MAX_R))
+                     and acqf.X_baseline.dim() == 2
+                     and _lib.fused_supported(X.shape[-2], acqf.X_baseline.shape[-2], acqf.sample_shape.numel())))
             and (not hasattr(acqf, "best_f") or acqf.best_f.numel() == 1))
 
 

@@ -50,7 +50,7 @@ extern "C" {
 
 #define MCACQ_MAX_Q 32
 #define MCACQ_MAX_D 64
-#define MCACQ_MAX_R 64
+#define MCACQ_MAX_R 512 /* baselines beyond 64 points are swept in 64-row chunks; see mcacq_fused_supported */
 #define MCACQ_MAX_SLICES 7 /* int8 contraction: at most 7 signed 8-bit slices (54-bit fixed-point operands) */
 
 /* info[b] bits written by mcacq_acq_forward (psd_safe_cholesky semantics, max_tries = 6):   */
@@ -209,6 +209,12 @@ int mcacq_slice_rows(const double* X, int64_t rows, int K, int64_t ldx, int Kp, 
                      int8_t* slices, double* row_scale, void* stream);
 int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G, const int8_t* A_slices, const double* row_scale,
                          const int8_t* B_slices, const double* col_scale, double* C, int64_t ldc, void* stream);
+
+/* 1 if mcacq_acq_forward / _backward take this shape (q points per q-batch, r baseline points, S MC samples; mc_mean != 0:
+ * the qUCB / qLCB / qPSTD utilities): the compiled limits AND the shared memory of the sample / reduce kernels, which grows
+ * with q * r.  Host-only (no CUDA call).  Shapes it rejects take the generic route of
+ * SampleReducingMCAcquisitionFunction (botorch/acquisition/monte_carlo.py:268-305) over mcacq_posterior.            */
+int mcacq_fused_supported(int q, int r, int S, int mc_mean);
 
 /* Workspace size of one forward(+backward) call.  `mcacq_workspace_bytes` is the bound over all contraction modes;
  * `mcacq_workspace_bytes_model` is exact for the model's mode (the FP64 DMMA mode carries no int8 slice buffers).   */
