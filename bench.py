@@ -481,14 +481,15 @@ def main():
             peak_equiv = 2.0 * bf16_peak / pairs
             return {"bound": "tensor", "kernel": f"ozaki_imma_kernel (tcgen05 kind::i8, G={G} forward launch)", "achieved": ach,
                     "slices_fwd_bwd": [int(st8.g_fwd), int(st8.g_bwd)], "mode_in_effect": st8.contraction,
-                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.59e9 * (M / 65536.0) * (G / 6.0),
+                    "peak": peak_equiv, "unit": "TFLOP/s", "frac": ach / peak_equiv, "traffic": 8.93e9 * (M / 65536.0) * (G / 6.0),
                     "peak_source": f"2 x bf16_tflops ({peak_src}) / {pairs} int8 slice products per fp64 multiply-add",
                     "launch_ms": ms, "alg_flops_per_launch": alg_flops, "int8_tops": ach * pairs,
                     "library_int8_gemm_tops_measured": lib_int8,
                     "frac_of_library_int8_gemm": (ach * pairs / lib_int8) if lib_int8 else None,
                     "fp64_dgemm_peak_measured": fp64_peak_tf,
-                    "traffic_source": "ncu --set full dram__bytes_read+write of the G=6 forward launch at M=65536 (6.47 + 2.12 GB, "
-                                      "profiles/r01_ncu_full_int8_mode.md; algorithmic: 1.7 GB slices + 2.15 GB output), scaled to this M and G"}
+                    "traffic_source": "ncu --set full dram__bytes_read+write of the G=6 forward launch at M=65536 (6.80 + 2.13 GB, "
+                                      "profiles/r02_ncu_full_c3_chunk_6_5_raw.csv; algorithmic: 1.7 GB slices + 2.15 GB output), "
+                                      "scaled to this M and G"}
 
         roof = {"int8": int8_roofline, "dmma": dmma_roofline}
         roofline = roof[args.contraction]()
