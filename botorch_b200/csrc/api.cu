@@ -35,6 +35,7 @@ int posterior_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st);
 int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 int info_summary(const int32_t* info, int64_t b, int32_t* out, cudaStream_t st);
+int transpose_panel(const double* src, int rows, int cols, double* dst, cudaStream_t st);
 size_t sample_reduce_fwd_smem(int q, int r, int S);
 size_t sample_reduce_bwd_smem(int q, int r, int S, bool mc_mean);
 
@@ -44,6 +45,7 @@ struct Workspace {
   int32_t* slice_exp;
   int8_t* slices;
   int32_t* counter;
+  double* AbT;   // [np x r] transposed baseline panel (r > 64: right operand of the backward baseline GEMM)
   size_t bytes;
 };
 
@@ -81,6 +83,7 @@ static Workspace carve(void* base, int64_t b, int q, int d, int np, int r, int i
   w.slice_exp = (int32_t*)take((size_t)M * 4);
   w.mean_part = (double*)take(int8_g ? (size_t)((np + 63) / 64) * M * 8 : 256);
   w.slices = (int8_t*)take(int8_g ? (size_t)int8_g * M * np : 256);
+  w.AbT = (double*)take(r > 64 ? (size_t)r * np * 8 : 256);
   w.bytes = off;
   return w;
 }
@@ -139,6 +142,7 @@ static int run_posterior_stage(const mcacq_model* m, const mcacq_baseline* base,
   bp.A_base = r > 0 ? base->A_base : nullptr;
   bp.U_base = r > 0 ? base->U_base : nullptr;
   bp.mean = w.mean; bp.Sxx = w.Sxx; bp.Sxb = w.Sxb;
+  bp.counter = w.counter;
   return posterior_blocks_fwd(bp, st);
 }
 
@@ -206,6 +210,17 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   bp.emit_slices = fuse_slices ? 1 : 0; bp.G = model->g_bwd;
   bp.slices = w.slices; bp.slice_scale = w.slice_scale; bp.slice_exp = w.slice_exp; bp.A_absmax = w.A_absmax;
   bp.Ab_absmax = r > 0 ? base->A_base_absmax : nullptr;
+  bp.T = nullptr;
+  // large baselines: the baseline term of dA as a plain GEMM, T = gSxb A_base (into the Kt buffer, which is free until the
+  // contraction below writes dKt there); odd r keeps the in-kernel loop (the 16-byte cp.async chunks need an even pitch)
+  {
+    const char* e = getenv("MCACQ_BIGR_GEMM");
+    if (r > 64 && (r & 1) == 0 && !(e != nullptr && atoi(e) == 0)) {
+      if ((rc = transpose_panel(base->A_base, r, model->np, w.AbT, st))) return rc;
+      if ((rc = mcacq_dgemm_nt(0, M, model->np, r, gSxb, r, w.AbT, r, w.Kt, model->np, w.counter, st))) return rc;
+      bp.T = w.Kt;
+    }
+  }
   if ((rc = posterior_blocks_bwd(bp, st))) return rc;
   if (model->contraction == 1) {
     if (!fuse_slices &&

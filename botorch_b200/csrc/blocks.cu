@@ -20,14 +20,48 @@ int posterior_blocks_fwd_q4(const BlocksParams& p, cudaStream_t st);
 
 static int posterior_blocks_fwd_chunk(const BlocksParams& p, cudaStream_t st);
 
-// Baselines beyond 64 points: the accumulators of the cross-Gram live in registers (8 row tiles at most), so the baseline is
-// swept in chunks of 64 rows, one launch per chunk.  The first launch also produces mean / Sxx / the row maxima; the others
-// only write their columns of Sxb.  Every Sxb entry is the same DMMA sequence over k as in a single-chunk launch.
+// Sxb[i][j] = s^2 (k(u_i, ub_j) - G[i][j]) in place over G = A A_base^T (same arithmetic as the tail of posterior_blocks_kernel)
+__global__ void cross_finish_kernel(BlocksParams p) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = p.b * p.q * (int64_t)p.r;
+  if (idx >= total) return;
+  const int64_t i = idx / p.r;
+  const int j = (int)(idx - i * p.r);
+  const double* ui = p.U + i * p.d;
+  const double* uj = p.U_base + (int64_t)j * p.d;
+  double sq = 0.0;
+  for (int k = 0; k < p.d; k++) {
+    const double df = ui[k] - uj[k];
+    sq = fma(df, df, sq);
+  }
+  p.Sxb[idx] = p.y_std * p.y_std * (kernel_value(p.kernel_id, p.outputscale, sq) - p.Sxb[idx]);
+}
+
+// Baselines beyond 64 points.  The accumulators of the cross-Gram live in registers (8 row tiles at most), and every warp
+// streams the baseline rows it contracts with from L2 -- at r = 256 that is an 8 MB panel per q-batch.  So the cross term
+// becomes what it is for a large baseline, a plain GEMM:  G = A A_base^T  ([b q x np] x [r x np]^T, the 64 x 64-tile DMMA
+// kernel of dgemm_nt.cu, whose tiles share the baseline panel through shared memory), finished in place by
+// `cross_finish_kernel`; mean / Sxx / the row maxima come from one r = 0 launch of the block kernel.  Without a scratch word
+// for the GEMM's tile counter (or with MCACQ_BIGR_GEMM=0) the baseline is swept in 64-row chunks instead, one block-kernel
+// launch per chunk (the first one also produces mean / Sxx, the others only their Sxb columns).
 int posterior_blocks_fwd(const BlocksParams& p0, cudaStream_t st) {
   BlocksParams p = p0;
   p.r_pitch = p0.r;
   p.cross_only = 0;
   if (p0.r <= 64) return posterior_blocks_fwd_chunk(p, st);
+  const char* e = getenv("MCACQ_BIGR_GEMM");
+  if (p0.counter != nullptr && !(e != nullptr && atoi(e) == 0)) {
+    p.r = 0; p.A_base = nullptr; p.U_base = nullptr; p.Sxb = nullptr;
+    int rc = posterior_blocks_fwd_chunk(p, st);
+    if (rc) return rc;
+    const int64_t M = p0.b * p0.q;
+    if ((rc = mcacq_dgemm_nt(0, M, p0.r, p0.np, p0.A, p0.np, p0.A_base, p0.np, p0.Sxb, p0.r, p0.counter, st))) return rc;
+    const int64_t total = M * p0.r;
+    cross_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p0);
+    count_launch();
+    MCACQ_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   for (int r0 = 0; r0 < p0.r; r0 += 64) {
     p.r = (p0.r - r0 < 64) ? p0.r - r0 : 64;
     p.A_base = p0.A_base + (int64_t)r0 * p0.np;

@@ -131,7 +131,25 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
         for (int t = 0; t < NT; t++) dmma884b(acc[mi][t][0], acc[mi][t][1], cb[mi][kk], rb[kk][t]);
       loadn<NT>(p.A_base + (int64_t)(kk * 4 + t4) * np + cn, kk * 4 + t4 < r && cn < col_end, rb[kk]);
     }
-    if (RLOOP) {
+    if (RLOOP && p.T != nullptr) {
+      // the baseline term was computed as a GEMM (T = gSxb A_base): the lane's 2 NT consecutive output columns of row g
+      const int oc0 = c0 + 2 * NT * t4;
+#pragma unroll
+      for (int mi = 0; mi < QT; mi++) {
+        const int i = mi * 8 + g;
+        if (i < q && oc0 < col_end) {
+          const double* src = p.T + (bb * q + i) * (int64_t)np + oc0;
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int t = 0; t < NT; t += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(src + e * NT + t);
+              acc[mi][t][e] = -s2 * v.x;
+              acc[mi][t + 1][e] = -s2 * v.y;
+            }
+        }
+      }
+    } else if (RLOOP) {
       const int cc = c0 + NT * g;   // this lane's source columns in the current step
 #pragma unroll 4
       for (int j0 = 0; j0 < r; j0 += 4) {
@@ -273,6 +291,29 @@ static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
   } else {
     posterior_blocks_bwd_kernel<QT, RT, 0, RLOOP><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
   }
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// dst[cols x rows] = src[rows x cols]^T (the baseline panel A_base, a few MB: once per backward call)
+__global__ void transpose_panel_kernel(const double* __restrict__ src, int rows, int cols, double* __restrict__ dst) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(int64_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+int transpose_panel(const double* src, int rows, int cols, double* dst, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_panel_kernel<<<grid, block, 0, st>>>(src, rows, cols, dst);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

@@ -23,6 +23,7 @@ struct BlocksParams {
   // U_base / Sxb point at the chunk's first row / column, `r_pitch` is the row pitch of Sxb (the whole baseline) and chunks
   // after the first only write their Sxb columns (`cross_only`)
   int r_pitch, cross_only;
+  int32_t* counter;     // 4-byte scratch word for the tile counter of the baseline GEMM (r > 64); nullptr: chunked sweep
 };
 
 struct BlocksBwdParams {
@@ -46,6 +47,8 @@ struct BlocksBwdParams {
   int32_t* slice_exp;         // [b*q]  scratch: exponent of the largest |dA[i][:]| (pass 1 -> pass 2)
   const double* A_absmax;     // [b*q]  max_k |A[i][k]| from the forward pass
   const double* Ab_absmax;    // [r]    max_k |A_base[j][k]|
+  // r > 64: the baseline term gSxb A_base as a plain GEMM, computed beforehand (nullptr: run-time loop in the kernel)
+  const double* T;            // [b*q x np]
 };
 
 struct SRParams {

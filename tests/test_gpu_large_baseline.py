@@ -99,3 +99,25 @@ def test_chunked_forward_equals_the_generic_route():
     gb, = torch.autograd.grad(vb.sum(), Xb)
     assert float(((va - vb).abs() / vb.abs()).max().detach()) < 1e-9
     assert float((ga - gb).abs().max() / gb.abs().max()) < 1e-7
+
+
+@pytest.mark.parametrize("mode", ["int8", "dmma"])
+def test_baseline_gemm_and_chunked_sweep_agree(mode):
+    """r > 64 runs the cross term / the baseline term of dA as plain GEMMs (dgemm_nt); MCACQ_BIGR_GEMM=0 selects the chunked
+    sweep / the in-kernel loop instead.  Different summation orders of the same fp64 sums: agreement to rounding."""
+    from botorch_b200 import settings
+
+    with settings.contraction(mode):
+        data, model, acqf, orc, X = _setup("C3", 512, 160, 8)
+        out = []
+        for flag in ("1", "0"):
+            os.environ["MCACQ_BIGR_GEMM"] = flag
+            try:
+                Xg = X.to(DEV).requires_grad_(True)
+                v = acqf(Xg)
+                (g,) = torch.autograd.grad(v.sum(), Xg)
+                out.append((v.detach(), g))
+            finally:
+                os.environ.pop("MCACQ_BIGR_GEMM", None)
+    assert float(((out[0][0] - out[1][0]).abs() / out[1][0].abs()).max()) < 1e-11
+    assert float((out[0][1] - out[1][1]).abs().max() / out[1][1].abs().max()) < (1e-9 if mode == "dmma" else 1e-7)
