@@ -99,6 +99,15 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
       if (t4 == 0 && i < q && chunk == 0) p.slice_scale[bb * q + i] = ldexp(1.0, ex + 2);
     }
   }
+  // acc * 2^shift as ONE multiplication (exact: a power of two, the product stays far inside the normal range) wherever
+  // 2^shift is representable; ldexp, whose range checks cost ~15 instructions per element, only for absurd row scales
+  double smul[QT];
+  bool sfast[QT];
+#pragma unroll
+  for (int mi = 0; mi < QT; mi++) {
+    sfast[mi] = shift[mi] > -1000 && shift[mi] < 1000;
+    smul[mi] = sfast[mi] ? __hiloint2double((1023 + shift[mi]) << 20, 0) : 1.0;
+  }
   const size_t slice_stride = (size_t)p.b * q * np;
   double* Ab = p.A + bb * q * np;
   // 8 * NT output columns per step as NT DMMA column tiles (NT = 4 for the small shapes, 2 when the coefficient
@@ -198,7 +207,8 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
             for (int e = 0; e < 2; e++)
 #pragma unroll
               for (int t = 0; t < NT; t++) {
-                const unsigned long long y = balanced_bytes(__double2ll_rn(ldexp(acc[mi][t][e], shift[mi])));
+                const double scaled = sfast[mi] ? acc[mi][t][e] * smul[mi] : ldexp(acc[mi][t][e], shift[mi]);
+                const unsigned long long y = balanced_bytes(__double2ll_rn(scaled));
                 if (NT == 4) Y[e][t] = y; else Y[0][e * 2 + t] = y;
               }
             int8_t* sdst = p.slices + ((size_t)(bb * q + i)) * np + oc;

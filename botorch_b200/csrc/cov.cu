@@ -64,6 +64,7 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
     int64_t gr = row0 + p;
     s1[k * CT + p] = (gr < m1) ? U1[gr * d + k] : 0.0;
   }
+  const int stage_p0 = tid / d, stage_k0 = tid - stage_p0 * d, stage_dq = 256 / d, stage_dr = 256 - stage_dq * d;
   double pm[4] = {0.0, 0.0, 0.0, 0.0};
   // 2^(8G - 2 - e): |shift| stays far inside the exponent range (0 < outputscale < 2^e is a kernel hyper-parameter)
   const double slice_mul = SLICES ? ldexp(1.0, 8 * G - 2 - fixed_exp) : 1.0;
@@ -71,10 +72,16 @@ cov_cross_kernel(int kernel_id, double outputscale, const double* __restrict__ U
   for (int ct = t_begin; ct < t_end; ct++) {
     const int col0 = ct * CT;
     __syncthreads();  // previous tile's reads of s2 are done (and s1 is staged on the first pass)
-    for (int idx = tid; idx < CT * d; idx += 256) {
-      int p = idx / d, k = idx - p * d;
-      int gc = col0 + p;
-      s2[k * CT + p] = (gc < m2) ? U2[(int64_t)gc * d + k] : 0.0;
+    {
+      // (point p, dimension k) of element idx = tid + 256 i without a division per element; its address is simply
+      // col0 * d + idx, the tile's rows being contiguous in the point-major operand
+      const double* src = U2 + (int64_t)col0 * d;
+      int pp = stage_p0, kk = stage_k0;
+      for (int idx = tid; idx < CT * d; idx += 256) {
+        s2[kk * CT + pp] = (col0 + pp < m2) ? src[idx] : 0.0;
+        kk += stage_dr; pp += stage_dq;
+        if (kk >= d) { kk -= d; pp++; }
+      }
     }
     __syncthreads();
 
@@ -203,16 +210,21 @@ cov_cross_bwd_kernel(int kernel_id, double outputscale, const double* __restrict
   double vacc[NTD][2];
 #pragma unroll
   for (int j = 0; j < NTD; j++) { vacc[j][0] = 0.0; vacc[j][1] = 0.0; }
+  const int stage_p0 = tid / d, stage_k0 = tid - stage_p0 * d, stage_dq = 256 / d, stage_dr = 256 - stage_dq * d;
 
   const int n_chunks = (col_chunk > 0) ? (int)gridDim.y : 1;
   const int col_begin = (col_chunk > 0) ? (int)blockIdx.y * col_chunk : 0;
   const int col_end = (col_chunk > 0 && (int)blockIdx.y + 1 < n_chunks) ? col_begin + col_chunk : m2;
   for (int c0 = col_begin; c0 < col_end; c0 += BW_T) {
     __syncthreads();  // previous tile's DMMA reads of s2 / sG are done
-    for (int idx = tid; idx < BW_T * d; idx += 256) {
-      int p = idx / d, k = idx - p * d;
-      int gc = c0 + p;
-      s2[k * BW_P + p] = (gc < col_end) ? U2[(int64_t)gc * d + k] : 0.0;
+    {
+      const double* src = U2 + (int64_t)c0 * d;   // element idx of the tile lives at c0 * d + idx (no division per element)
+      int pp = stage_p0, kk = stage_k0;
+      for (int idx = tid; idx < BW_T * d; idx += 256) {
+        s2[kk * BW_P + pp] = (c0 + pp < col_end) ? src[idx] : 0.0;
+        kk += stage_dr; pp += stage_dq;
+        if (kk >= d) { kk -= d; pp++; }
+      }
     }
     for (int p = tid; p < BW_T; p += 256) {
       int gc = c0 + p;

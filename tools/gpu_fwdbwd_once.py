@@ -24,9 +24,12 @@ for _ in range(reps):
     (g,) = torch.autograd.grad(v.sum(), Xg)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+prof_last = os.environ.get("MCACQ_PROFILE_LAST") == "1"   # ncu --profile-from-start off: only the timed pass is captured
+if prof_last: torch.cuda.profiler.start()
 e0.record()
 Xg = X.detach().requires_grad_(True)
 v = acqf(Xg)
 (g,) = torch.autograd.grad(v.sum(), Xg)
 e1.record(); torch.cuda.synchronize()
+if prof_last: torch.cuda.profiler.stop()
 print(f"{cfg} b={b}: fwd+bwd {e0.elapsed_time(e1):.3f} ms")
