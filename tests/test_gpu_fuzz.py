@@ -20,6 +20,8 @@ def _case(seed: int):
     q = ri(1, 6) if seed % 5 else ri(7, 32)
     r = 0 if seed % 3 == 0 else (ri(1, 24) if seed % 7 else ri(25, 64))
     S, b = ri(1, 300), ri(1, 23)
+    if seed % 11 == 5 and r > 0:   # baselines beyond 64 points: the GEMM (even r) / run-time loop (odd r) posterior-block routes
+        r, q = ri(65, 220), min(q, 12)
     return dict(n=n, d=d, q=q, r=r, S=S, b=b, kernel="rbf" if seed % 2 else "matern52", scale=seed % 4 == 1,
                 normalize=seed % 3 == 1, fixed_noise=seed % 5 == 2, fat=seed % 6 != 3,
                 contraction="int8" if seed % 2 == 0 else "dmma", g=g)
