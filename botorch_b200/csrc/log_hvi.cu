@@ -17,6 +17,8 @@
 // weights w_c * d(logdiffexp)/d(E|O) * exp(area - E|O), and accumulates d out / d obj[j][k] one objective at a time.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mcacq {
@@ -156,8 +158,8 @@ __device__ __forceinline__ double hv_area(const double (&li)[QMAX * MMAX], const
 template <int QMAX>
 struct HvMasks { static constexpr bool UNROLL = QMAX <= 4; static constexpr unsigned NM = 1u << QMAX; };
 
-template <int QMAX, int MMAX>
-__global__ void __launch_bounds__(128)
+template <int QMAX, int MMAX, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 log_hvi_fwd_kernel(const double* __restrict__ obj, const double* __restrict__ cl, const double* __restrict__ lcl, int64_t B, int q,
                    int m, int nc, double tau_relu, double tau_max, double* __restrict__ out) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -209,8 +211,8 @@ log_hvi_fwd_kernel(const double* __restrict__ obj, const double* __restrict__ cl
 // Backward, q <= 4: per cell (1) all subset areas (kept in registers) and the parity sums, (2) the subset weights
 // w_c * d(logdiffexp)/d(E|O) * exp(area - E|O), (3) one objective k at a time, every subset's fatmin gradients weighted into
 // d / d li[:, k].  The areas are evaluated once; only the (cheap, rational) fatmin weights are evaluated a second time.
-template <int QMAX, int MMAX>
-__global__ void __launch_bounds__(128)
+template <int QMAX, int MMAX, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 log_hvi_bwd_kernel(const double* __restrict__ gout, const double* __restrict__ outv, const double* __restrict__ obj,
                    const double* __restrict__ cl, const double* __restrict__ lcl, int64_t B, int q, int m, int nc,
                    double tau_relu, double tau_max, double* __restrict__ gobj) {
@@ -341,10 +343,18 @@ static int log_hvi_launch(int backward, const double* gout, const double* outv, 
                           const double* lcl, int64_t B, int q, int m, int nc, double tau_relu, double tau_max, double* out,
                           cudaStream_t st) {
   const unsigned blocks = (unsigned)((B + 127) / 128);
-  if (backward)
-    log_hvi_bwd_kernel<QMAX, MMAX><<<blocks, 128, 0, st>>>(gout, outv, obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out);
-  else
-    log_hvi_fwd_kernel<QMAX, MMAX><<<blocks, 128, 0, st>>>(obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out);
+  // resident CTAs per SM the register allocation aims at.  The kernels are latency-bound, so occupancy beats spills: backward
+  // (q = m = 4) 2 CTAs = 234 registers, no spills: 45.0 ms per 524288 samples x 32 cells; 3 = 168 registers + 216-byte stack:
+  // 32.6 ms; 4 = 128 registers + 368 bytes: 30.8 ms (default); 5 / 6 = 96 / 80 registers: 33.0 / 34.8 ms.  Forward: 112
+  // registers at 4 (12.9 ms), spilling at 5 / 6 (14.7 / 15.1 ms).  MCACQ_HVI_MINB = 2 | 3 selects the other backward builds.
+  static const int minb = getenv("MCACQ_HVI_MINB") ? atoi(getenv("MCACQ_HVI_MINB")) : 4;
+#define HV_BWD(MB) log_hvi_bwd_kernel<QMAX, MMAX, MB><<<blocks, 128, 0, st>>>(gout, outv, obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out)
+  if (backward) {
+    if (minb <= 2) HV_BWD(2); else if (minb == 3) HV_BWD(3); else HV_BWD(4);
+  } else {
+    log_hvi_fwd_kernel<QMAX, MMAX, 4><<<blocks, 128, 0, st>>>(obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out);
+  }
+#undef HV_BWD
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
