@@ -75,7 +75,7 @@ EXPORTS = [
     "mcacq_last_launch_count", "mcacq_sobol_draw", "mcacq_log_areas_forward", "mcacq_log_areas_backward", "mcacq_log_hvi_forward", "mcacq_log_hvi_backward", "mcacq_dgemm_nt", "mcacq_syrk_sub", "mcacq_lower_times_few", "mcacq_slice_rows",
     "mcacq_ozaki_contract", "mcacq_cov_cross_sliced", "mcacq_workspace_bytes_model",
     "mcacq_sample_reduce_forward", "mcacq_info_summary", "mcacq_lbfgsb_state_bytes", "mcacq_lbfgsb_init", "mcacq_lbfgsb_step", "mcacq_lbfgsb_summary",
-    "mcacq_fused_supported",
+    "mcacq_fused_supported", "mcacq_fast_math_probe",
 ]
 
 
@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
     L.mcacq_num_sms.restype = i32
     L.mcacq_last_launch_count.restype = i32
     L.mcacq_sobol_draw.argtypes = [vp, vp, i32, i64, i64, vp, vp]
+    L.mcacq_fast_math_probe.argtypes = [i32, vp, vp, i64, vp]
+    L.mcacq_fused_supported.argtypes = [i32, i32, i32, i32]
     L.mcacq_scale_inputs.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
     L.mcacq_cov_cross.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp]
     L.mcacq_cov_cross_bwd.argtypes = [i32, dbl, vp, i64, vp, i32, i32, vp, i64, vp, vp, vp, i32, vp]

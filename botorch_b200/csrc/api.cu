@@ -279,6 +279,21 @@ static void fill_sr(SRParams& sp, const mcacq_baseline* base, const mcacq_mc* mc
   sp.gmean = w.gmean; sp.gSxx = w.gSxx; sp.gSxb = w.gSxb;
 }
 
+// y[i] = f(x[i]) with the kernels' own FP64 elementary functions (fast_math.cuh): kind 0 exp, 1 log, 2 log1p (x >= 0)
+__global__ void fast_math_probe_kernel(int kind, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  y[i] = kind == 0 ? fm_exp(v) : kind == 1 ? fm_log(v) : fm_log1p_nonneg(v);
+}
+
+extern "C" int mcacq_fast_math_probe(int kind, const double* x, double* y, int64_t n, void* stream) {
+  if (kind < 0 || kind > 2 || !x || !y || n < 0) return MCACQ_EINVAL;
+  if (n == 0) return 0;
+  fast_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, x, y, n);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mcacq_fused_supported(int q, int r, int S, int mc_mean) {
   if (q <= 0 || q > MCACQ_MAX_Q || r < 0 || r > MCACQ_MAX_R || S <= 0) return 0;
   const size_t limit = 200 * 1024;   // what the sample / reduce launchers accept

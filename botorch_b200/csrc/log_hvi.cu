@@ -35,12 +35,12 @@ __device__ __forceinline__ double hv_rcp(double x) {
 
 __device__ __forceinline__ double hv_softplus(double y) {
   if (y > 20.0) return y;
-  if (y < -20.0) return exp(y);
-  return log1p(exp(y));
+  if (y < -20.0) return fm_exp(y);
+  return fm_log1p_nonneg(fm_exp(y));
 }
 __device__ __forceinline__ double hv_sigmoid(double y) {
-  if (y >= 0.0) { const double e = exp(-y); return 1.0 / (1.0 + e); }
-  const double e = exp(y);
+  if (y >= 0.0) { const double e = fm_exp(-y); return 1.0 / (1.0 + e); }
+  const double e = fm_exp(y);
   return e / (1.0 + e);
 }
 template <bool GRAD>
@@ -52,7 +52,7 @@ __device__ __forceinline__ double hv_log_fatplus(double x, double tau, double in
   const double tf = tau * f;
   if (!(tf > 0.0)) { if (GRAD) grad = 0.0; return -1e30; }
   if (GRAD) grad = (hv_sigmoid(y) - 0.2 * y * cy * cy) / tf;
-  return log(tf);
+  return fm_log(tf);
 }
 
 // fatmin over the members of `mask` of column k of li (QMAX x MMAX, row-major in registers); gw[j] = d / d li[j][k].
@@ -91,7 +91,7 @@ __device__ __forceinline__ double hv_fatmin_masked(const double (&li)[QMAX * MMA
     for (int j = 0; j < QMAX; j++)
       gw[j] = ((mask >> j) & 1u) ? ((j == ami) ? 1.0 + (S_pd + 1.0) * rS : -pd[j] * rS) : 0.0;
   }
-  return mn - tau * log(S);
+  return mn - tau * fm_log(S);
 }
 
 // fatmin of the pair (a, b); g0 = d / d a.  The smaller entry contributes exactly 2 / 2 = 1 to the sum.
@@ -109,7 +109,7 @@ __device__ __forceinline__ double hv_fatmin2(double a, double b, double tau, dou
     const double rS = hv_rcp(S);
     g0 = a_min ? 1.0 + (p_min + p_other + 1.0) * rS : -p_other * rS;
   }
-  return mn - tau * log(S);
+  return mn - tau * fm_log(S);
 }
 
 // streaming log-sum-exp with the inf conventions of safe_math.logsumexp (an infinite maximum wins; -inf terms vanish)
@@ -118,10 +118,10 @@ struct HvLse {
   __device__ __forceinline__ void init() { m = -CUDART_INF; s = 0.0; }
   __device__ __forceinline__ void push(double v) {
     if (v == -CUDART_INF) return;
-    if (v > m) { s = (m == -CUDART_INF) ? 1.0 : s * exp(m - v) + 1.0; m = v; }
-    else s += exp(v - m);
+    if (v > m) { s = (m == -CUDART_INF) ? 1.0 : s * fm_exp(m - v) + 1.0; m = v; }
+    else s += fm_exp(v - m);
   }
-  __device__ __forceinline__ double value() const { return (m == -CUDART_INF) ? m : (isinf(m) ? m : m + log(s)); }
+  __device__ __forceinline__ double value() const { return (m == -CUDART_INF) ? m : (isinf(m) ? m : m + fm_log(s)); }
 };
 
 // logdiffexp(log_a = E, log_b = O) = O + log1mexp(E - O)   (safe_math.py:106-120, 36-46); dE, dO: partial derivatives
@@ -262,13 +262,13 @@ log_hvi_bwd_kernel(const double* __restrict__ gout, const double* __restrict__ o
       double dE, dO;
       const double dc = hv_logdiffexp<true>(E, O, dE, dO);
       if (dc == -CUDART_INF || isnan(dc)) continue;
-      const double wc = g_up * exp(dc - total);          // softmax weight of the cell in the outer log-sum-exp
+      const double wc = g_up * fm_exp(dc - total);          // softmax weight of the cell in the outer log-sum-exp
       if (wc == 0.0) continue;
 #pragma unroll
       for (unsigned mask = 1; mask < NM; mask++) {
         const bool odd = __popc(mask) & 1;
         const double ref = odd ? O : E;
-        ws[mask] = (mask < n_masks && ws[mask] != -CUDART_INF && ref != -CUDART_INF) ? wc * (odd ? dO : dE) * exp(ws[mask] - ref) : 0.0;
+        ws[mask] = (mask < n_masks && ws[mask] != -CUDART_INF && ref != -CUDART_INF) ? wc * (odd ? dO : dE) * fm_exp(ws[mask] - ref) : 0.0;
       }
 #pragma unroll
       for (int k = 0; k < MMAX; k++) {
@@ -307,14 +307,14 @@ log_hvi_bwd_kernel(const double* __restrict__ gout, const double* __restrict__ o
       double dE, dO;
       const double dc = hv_logdiffexp<true>(E, O, dE, dO);
       if (dc == -CUDART_INF || isnan(dc)) continue;
-      const double wc = g_up * exp(dc - total);
+      const double wc = g_up * fm_exp(dc - total);
       if (wc == 0.0) continue;
       for (unsigned mask = 1; mask < n_masks; mask++) {
         const int n = __popc(mask);
         const double area = hv_area<QMAX, MMAX, true>(li, ll, m, mask, n, tau_max, inv_tm, ga);
         const double ref = (n & 1) ? O : E;
         if (area == -CUDART_INF || ref == -CUDART_INF) continue;
-        const double w = wc * ((n & 1) ? dO : dE) * exp(area - ref);
+        const double w = wc * ((n & 1) ? dO : dE) * fm_exp(area - ref);
 #pragma unroll
         for (int j = 0; j < QMAX; j++)
 #pragma unroll

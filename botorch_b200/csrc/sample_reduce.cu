@@ -287,7 +287,7 @@ sample_reduce_fwd_kernel(SRParams p) {
     if (fat >= 2) res = s / (double)S;
     else if (S == 0 || m == -CUDART_INF) res = -CUDART_INF;
     else if (isinf(m)) res = m;
-    else res = m + log(s) - log((double)S);
+    else res = m + fm_log(s) - fm_log((double)S);
     if (s_info & MCACQ_INFO_NOT_PSD) res = CUDART_NAN;
     p.acq[bb] = res;
     p.info[bb] = s_info | (s_nonfinite ? MCACQ_INFO_NONFINITE : 0);

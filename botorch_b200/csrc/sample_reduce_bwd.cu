@@ -99,7 +99,7 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
           double ws;
           if (fat >= 2) ws = gout / (double)S;
           else if (isinf(fm)) ws = (fm > 0) ? gout : ((isinf(lse_total) && lse_total < 0) ? gout : 0.0);
-          else ws = gout * exp(fm - lse_total);
+          else ws = gout * fm_exp(fm - lse_total);
           double* gys = gy + (size_t)(s0 + ns - c0) * GP;
 #pragma unroll
           for (int i = 0; i < QMAX; i++) if (i < q) gys[i] = ws * w[i] * dli[i];

@@ -43,7 +43,7 @@ __device__ __forceinline__ double log_improve(double z, double tau, double inv_t
   }
   if (fat == 4) {
     const double u = z * inv_tau;
-    const double sg = (u >= 0.0) ? 1.0 / (1.0 + exp(-u)) : exp(u) / (1.0 + exp(u));
+    const double sg = (u >= 0.0) ? 1.0 / (1.0 + fm_exp(-u)) : fm_exp(u) / (1.0 + fm_exp(u));
     if (GRAD) dli = sg * (1.0 - sg) * inv_tau;
     return sg;
   }
@@ -55,8 +55,8 @@ __device__ __forceinline__ double log_improve(double z, double tau, double inv_t
     } else if (u < -746.0) {  // exp(u) == 0 exactly in fp64
       sp = 0.0; dsp = 0.0;
     } else {
-      const double e = exp(u);
-      sp = log1p(e);
+      const double e = fm_exp(u);
+      sp = fm_log1p_nonneg(e);
       dsp = e / (e + 1.0);
     }
     const double den = fma(u, u, 1.0);
@@ -64,7 +64,7 @@ __device__ __forceinline__ double log_improve(double z, double tau, double inv_t
     const double f = sp + 0.1 * ca;
     const double tf = tau * f;
     if (GRAD) dli = (dsp - 0.2 * u * ca * ca) * ((tf > 1e-300 && tf < 1e300) ? fast_rcp(tf) : 1.0 / tf);
-    return log(tf);
+    return fm_log(tf);
   } else {
     const double xt = z / tau;
     if (xt > -35.0) {
@@ -72,12 +72,12 @@ __device__ __forceinline__ double log_improve(double z, double tau, double inv_t
       const double xb = z * beta;
       double sp, dsp;
       if (xb > 32.0) { sp = z; dsp = 1.0; }
-      else { const double e = exp(xb); sp = log1p(e) / beta; dsp = e / (e + 1.0); }
+      else { const double e = fm_exp(xb); sp = fm_log1p_nonneg(e) / beta; dsp = e / (e + 1.0); }
       if (GRAD) dli = dsp / sp;
-      return log(sp);
+      return fm_log(sp);
     } else {
       if (GRAD) dli = 1.0 / tau;
-      return xt + log(tau);
+      return xt + fm_log(tau);
     }
   }
 }
@@ -92,18 +92,18 @@ __device__ __forceinline__ double log_feas_term(double u, int fat, double& dlf) 
     if (u < 0.0) {
       const double a = u - c3, den = fma(a, a, 1.0);
       dlf = -2.0 * a / den;
-      return log((2.0 / 3.0) / den);
+      return fm_log((2.0 / 3.0) / den);
     }
     const double bb = u + c3, den = fma(bb, bb, 1.0);
     const double fv = 1.0 - (2.0 / 3.0) / den;
     dlf = ((4.0 / 3.0) * bb / (den * den)) / fv;
-    return log(fv);
+    return fm_log(fv);
   }
   // logexpit(u) = -log1pexp(-u) (safe_math.py:96-98, 78-93: log1p(exp(x)) for x <= 18, x + exp(-x) above)
   const double x = -u;
   double l1p, sig;   // log1pexp(x), sigmoid(x) = d log1pexp / dx
-  if (x <= 18.0) { const double e = exp(x); l1p = log1p(e); sig = e / (1.0 + e); }
-  else { const double e = exp(-x); l1p = x + e; sig = 1.0 - e; }
+  if (x <= 18.0) { const double e = fm_exp(x); l1p = fm_log1p_nonneg(e); sig = e / (1.0 + e); }
+  else { const double e = fm_exp(-x); l1p = x + e; sig = 1.0 - e; }
   dlf = sig;         // d(-log1pexp(-u)) / du = sigmoid(-u)
   return -l1p;
 }
@@ -139,7 +139,7 @@ __device__ __forceinline__ double sr_element(const SRParams& p, double yi, doubl
       dlf += dk * (-p.con_a[k] / p.con_eta[k]);
     }
     if (p.fat <= 1) { val += lf; dy += dlf; }          // log family: add the log-indicator (monte_carlo.py:322-348)
-    else { const double F = exp(lf); dy = dy * F + val * F * dlf; dm *= F; val *= F; }
+    else { const double F = fm_exp(lf); dy = dy * F + val * F * dlf; dm *= F; val *= F; }
   }
   return val;
 }
@@ -194,13 +194,13 @@ __device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, doub
 #pragma unroll
       for (int i = 0; i < QMAX; i++) if (i < q) w[i] = ((li[i] == M) ? head : 0.0) - dp[i] / P;
     }
-    return M + tau * log(P);
+    return M + tau * fm_log(P);
   } else {
     const double Mt = M / tau;
     double ssum = 0.0;
 #pragma unroll
     for (int i = 0; i < QMAX; i++) if (i < q) {
-      const double e = exp(li[i] / tau - Mt);
+      const double e = fm_exp(li[i] / tau - Mt);
       ssum += e;
       if (GRAD) w[i] = e;
     }
@@ -208,21 +208,21 @@ __device__ __forceinline__ double q_reduce(const double (&li)[QMAX], int q, doub
 #pragma unroll
       for (int i = 0; i < QMAX; i++) if (i < q) w[i] /= ssum;
     }
-    return (Mt + log(ssum)) * tau;
+    return (Mt + fm_log(ssum)) * tau;
   }
 }
 
 __device__ __forceinline__ void lse_push(double& m, double& s, double f) {
   if (f == -CUDART_INF) return;
-  if (f > m) { s = s * exp(m - f) + 1.0; m = f; }
-  else s += exp(f - m);
+  if (f > m) { s = s * fm_exp(m - f) + 1.0; m = f; }
+  else s += fm_exp(f - m);
 }
 __device__ __forceinline__ void lse_merge(double& m, double& s, double m2, double s2) {
   const double M = fmax(m, m2);
   if (M == -CUDART_INF) { m = M; s = 0.0; return; }
   if (isinf(M)) { m = M; s = 1.0; return; }
-  const double a = (m == -CUDART_INF) ? 0.0 : s * exp(m - M);
-  const double c = (m2 == -CUDART_INF) ? 0.0 : s2 * exp(m2 - M);
+  const double a = (m == -CUDART_INF) ? 0.0 : s * fm_exp(m - M);
+  const double c = (m2 == -CUDART_INF) ? 0.0 : s2 * fm_exp(m2 - M);
   m = M; s = a + c;
 }
 

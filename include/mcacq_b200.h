@@ -216,6 +216,11 @@ int mcacq_ozaki_contract(int tri_mode, int64_t M, int N, int K, int G, const int
  * SampleReducingMCAcquisitionFunction (botorch/acquisition/monte_carlo.py:268-305) over mcacq_posterior.            */
 int mcacq_fused_supported(int q, int r, int S, int mc_mean);
 
+/* y[i] = f(x[i]) evaluated with the kernels' own FP64 elementary functions (csrc/fast_math.cuh; kind 0: exp, 1: log,
+ * 2: log1p for x >= 0) -- what `torch.exp / log / log1p` are to the reference's safe_math (utils/safe_math.py:298-355).
+ * Test hook: lets the parity suite bound their error (<= 2.5 ulp) on the device itself.                              */
+int mcacq_fast_math_probe(int kind, const double* x, double* y, int64_t n, void* stream);
+
 /* Workspace size of one forward(+backward) call.  `mcacq_workspace_bytes` is the bound over all contraction modes;
  * `mcacq_workspace_bytes_model` is exact for the model's mode (the FP64 DMMA mode carries no int8 slice buffers).   */
 size_t mcacq_workspace_bytes(int64_t b, int q, int d, int np, int r);
