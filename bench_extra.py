@@ -408,14 +408,38 @@ def run_c5(args, ClockSampler, impl_reference=False):
         fp64_peak = _dgemm_peak(dev)
         strat = acqf.model.models[0].prediction_strategy()
         M = chunk * q
+        # Dominant kernel of this configuration: the backward of the fused log-HVI kernel (two thirds of a chunk).  It is bound by
+        # the FP64 ALU pipe -- elementary functions, no tensor-core or HBM work -- so its roofline is the FP64 instruction rate:
+        # executed FP64 warp instructions per (sample, cell) as counted by ncu for this build (`smsp__inst_executed_pipe_fp64`,
+        # profiles/r02_hvi_counts.csv: 3.15e9 forward / 6.56e9 backward per 524288 samples x 32 cells), 32 lanes x 2 flop each
+        # (the convention of the DFMA peak), over the kernel's own device time measured live here; peak = the DFMA rate of the
+        # FP64 pipe (tools/ubench_fp64, profiles/r01_ubench_fp64_pipe.txt).
+        FP64_WARP_INSTR_PER_SAMPLE_CELL = {"fwd": 3149674153.0 / (524288 * 32), "bwd": 6560018639.0 / (524288 * 32)}
+        FP64_PIPE_PEAK_TF = 34.1
+        n_cells = int(prob["nc"])
+        pairs_sc = float(chunk) * S * n_cells
+        bwd_ms = sum(r[1] for r in rows if "log_hvi_bwd" in r[0])
+        fwd_ms = sum(r[1] for r in rows if "log_hvi_fwd" in r[0])
+        exact_counts = (q == 4 and prob["m"] == 4)          # the counted build: q = m = 4
+        ach = (FP64_WARP_INSTR_PER_SAMPLE_CELL["bwd"] * pairs_sc * 64.0 / (bwd_ms * 1e-3) * 1e-12) if (bwd_ms > 0 and exact_counts) else None
         contraction_flops = 2.0 * prob["m"] * float(M) * strat.np * (strat.np + 1)   # forward + backward, m outputs, triangular-aware
         cont_ms = sum(r[1] for r in rows if "ozaki" in r[0] or "dgemm_tri" in r[0])
-        ach = contraction_flops / (cont_ms * 1e-3) * 1e-12 if cont_ms > 0 else None
-        roofline = {"bound": "tensor", "kernel": "the 2 x m contractions K R / dA R^T of one chunk (" + strat.contraction + " mode)",
-                    "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach / fp64_peak) if ach else None, "traffic": None,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run; the int8 mode runs the fp64 contraction on the INT8 tensor pipe, "
-                                   "so fp64-equivalent rates above the DGEMM peak are possible",
-                    "launch_ms": cont_ms, "alg_flops_per_launch": contraction_flops,
+        roofline = {"bound": "fp64-alu", "kernel": "log_hvi_bwd_kernel (inclusion-exclusion loop of qLogEHVI, hand-written backward): FP64 "
+                                                    "elementary functions, no tensor-core / HBM work",
+                    "achieved": ach, "peak": FP64_PIPE_PEAK_TF, "unit": "TFLOP/s", "frac": (ach / FP64_PIPE_PEAK_TF) if ach else None,
+                    "traffic": 77375232 + 41262336,
+                    "traffic_source": "ncu dram__bytes_read + write of one backward launch (profiles/r02_hvi_counts.csv): the kernel is compute-bound",
+                    "peak_source": "DFMA rate of the FP64 pipe measured on this pool (profiles/r01_ubench_fp64_pipe.txt); achieved = executed FP64 "
+                                   "instructions (ncu count per sample x cell of this build) x 64 flop / live kernel time",
+                    "launch_ms": bwd_ms, "forward_launch_ms": fwd_ms,
+                    "forward_frac": (FP64_WARP_INSTR_PER_SAMPLE_CELL["fwd"] * pairs_sc * 64.0 / (fwd_ms * 1e-3) * 1e-12 / FP64_PIPE_PEAK_TF)
+                    if (fwd_ms > 0 and exact_counts) else None,
+                    "contractions": {"kernel": "the 2 x m contractions K R / dA R^T of one chunk (" + strat.contraction + " mode)",
+                                     "ms": cont_ms, "alg_flops": contraction_flops,
+                                     "fp64_equivalent_tflops": contraction_flops / (cont_ms * 1e-3) * 1e-12 if cont_ms > 0 else None,
+                                     "fp64_dgemm_peak_measured": fp64_peak,
+                                     "note": "int8 mode: the fp64 contraction runs on the INT8 tensor pipe, fp64-equivalent rates above the "
+                                             "DGEMM peak are expected (headline roofline: bench.py default config)"},
                     "chunk_kernel_ms_total": tot, "own_kernel_share_of_chunk": own / tot}
         cpu = None
         if world == 1:
