@@ -165,7 +165,15 @@ def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """The current CUDA stream of the current device as a `cudaStream_t` value.  `torch.cuda.current_stream()` builds a Python
+    Stream object through several device-index look-ups (~25 us, three to four times per optimiser round); the raw accessor
+    returns the same handle in ~1 us."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
