@@ -36,6 +36,8 @@ int sample_reduce_fwd(const SRParams& p, cudaStream_t st);
 int sample_reduce_bwd(const SRParams& p, cudaStream_t st);
 int info_summary(const int32_t* info, int64_t b, int32_t* out, cudaStream_t st);
 int transpose_panel(const double* src, int rows, int cols, double* dst, cudaStream_t st);
+bool baseline_direct_fits(int q, int r);
+int baseline_direct_bwd(const BlocksBwdParams& p, cudaStream_t st);
 size_t sample_reduce_fwd_smem(int q, int r, int S);
 size_t sample_reduce_bwd_smem(int q, int r, int S, bool mc_mean);
 
@@ -211,6 +213,7 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
   bp.slices = w.slices; bp.slice_scale = w.slice_scale; bp.slice_exp = w.slice_exp; bp.A_absmax = w.A_absmax;
   bp.Ab_absmax = r > 0 ? base->A_base_absmax : nullptr;
   bp.T = nullptr;
+  bp.skip_base_direct = 0;
   // large baselines: the baseline term of dA as a plain GEMM, T = gSxb A_base (into the Kt buffer, which is free until the
   // contraction below writes dKt there); odd r keeps the in-kernel loop (the 16-byte cp.async chunks need an even pitch)
   {
@@ -219,9 +222,11 @@ static int run_posterior_backward(const mcacq_model* model, const mcacq_baseline
       if ((rc = transpose_panel(base->A_base, r, model->np, w.AbT, st))) return rc;
       if ((rc = mcacq_dgemm_nt(0, M, model->np, r, gSxb, r, w.AbT, r, w.Kt, model->np, w.counter, st))) return rc;
       bp.T = w.Kt;
+      bp.skip_base_direct = baseline_direct_fits(q, r) ? 1 : 0;
     }
   }
   if ((rc = posterior_blocks_bwd(bp, st))) return rc;
+  if (bp.skip_base_direct && (rc = baseline_direct_bwd(bp, st))) return rc;
   if (model->contraction == 1) {
     if (!fuse_slices &&
         (rc = mcacq_slice_rows(w.A, M, model->np, model->np, model->np, model->g_bwd, 0, 0, w.slices, w.slice_scale, st)))

@@ -265,7 +265,7 @@ posterior_blocks_bwd_kernel(BlocksBwdParams p, int col_chunk) {
       double w = s2 * (gxx[i * q + j] + gxx[j * q + i]) * kernel_dfactor(p.kernel_id, p.outputscale, sq);
       accu = fma(w, Ub[i * d + k] - Ub[j * d + k], accu);
     }
-    for (int j = 0; j < r; j++) {
+    for (int j = 0; j < (p.skip_base_direct ? 0 : r); j++) {
       double sq = 0.0;
       for (int kk = 0; kk < d; kk++) {
         double df = Ub[i * d + kk] - p.U_base[j * d + kk];
@@ -301,6 +301,54 @@ static int launch_blocks_bwd(const BlocksBwdParams& p, cudaStream_t st) {
   } else {
     posterior_blocks_bwd_kernel<QT, RT, 0, RLOOP><<<(unsigned)blocks, BLK_WARPS * 32, 0, st>>>(p, col_chunk);
   }
+  count_launch();
+  MCACQ_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// Direct K(X, X_base) terms of dU for large baselines:  dU[i][k] += sum_j w_ij (u_ik - ub_jk),  w_ij = s^2 gSxb[i][j] g(|u_i - ub_j|^2).
+// The tail of the block kernel evaluates them with one warp per q-batch and recomputes the distance for every (i, k): O(q d r d).
+// Here a CTA per q-batch first parks the q x r weights in shared memory (one distance each), then every (i, k) sums over j.
+__global__ void __launch_bounds__(128)
+baseline_direct_bwd_kernel(BlocksBwdParams p) {
+  extern __shared__ __align__(16) double wsm[];   // [q][r]
+  const int64_t bb = blockIdx.x;
+  const int q = p.q, r = p.r, d = p.d, tid = threadIdx.x;
+  const double s2 = p.y_std * p.y_std;
+  const double* Ub = p.U + bb * q * d;
+  const double* gxb = p.gSxb + bb * q * r;
+  for (int idx = tid; idx < q * r; idx += 128) {
+    const int i = idx / r, j = idx - i * r;
+    double sq = 0.0;
+    for (int kk = 0; kk < d; kk++) {
+      const double df = Ub[i * d + kk] - p.U_base[j * d + kk];
+      sq = fma(df, df, sq);
+    }
+    wsm[idx] = s2 * gxb[idx] * kernel_dfactor(p.kernel_id, p.outputscale, sq);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < q * d; idx += 128) {
+    const int i = idx / d, k = idx - i * d;
+    const double uik = Ub[i * d + k];
+    double accu = 0.0;
+    for (int j = 0; j < r; j++) accu = fma(wsm[i * r + j], uik - p.U_base[j * d + k], accu);
+    p.dU[(bb * q + i) * d + k] += accu;
+  }
+}
+
+constexpr size_t BASE_DIRECT_SMEM_MAX = 160 * 1024;
+bool baseline_direct_fits(int q, int r) { return (size_t)q * r * sizeof(double) <= BASE_DIRECT_SMEM_MAX; }
+
+int baseline_direct_bwd(const BlocksBwdParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.q * p.r * sizeof(double);
+  if (smem > BASE_DIRECT_SMEM_MAX) return MCACQ_ELIMIT;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(baseline_direct_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BASE_DIRECT_SMEM_MAX);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  baseline_direct_bwd_kernel<<<(unsigned)p.b, 128, smem, st>>>(p);
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;

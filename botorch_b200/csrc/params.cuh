@@ -49,6 +49,7 @@ struct BlocksBwdParams {
   const double* Ab_absmax;    // [r]    max_k |A_base[j][k]|
   // r > 64: the baseline term gSxb A_base as a plain GEMM, computed beforehand (nullptr: run-time loop in the kernel)
   const double* T;            // [b*q x np]
+  int skip_base_direct;       // 1: the direct K(X, X_base) terms of dU are added by baseline_direct_bwd_kernel afterwards
 };
 
 struct SRParams {
