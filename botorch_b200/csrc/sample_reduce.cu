@@ -51,15 +51,36 @@ sample_reduce_fwd_kernel(SRParams p) {
   __syncthreads();
 
   // ---- B = Sxb L^{-T}: forward substitution, one warp per row, lanes over the dot product
-  for (int i = warp; i < q; i += NW) {
-    double* bi = brow + (size_t)i * r;
+  // The rows a warp owns (warp, warp + NW, ...) advance TOGETHER through the substitution: every factor entry is loaded once
+  // for all of them and their shuffle trees overlap, so the serial chain is r steps per warp instead of r per row.  Per row
+  // the arithmetic (lane-strided partial sums, xor tree) is unchanged.
+  {
+    constexpr int RPW = (QMAX + NW - 1) / NW;
     for (int j = 0; j < r; j++) {
       const double* Lj = p.L_base + (size_t)j * r;
-      double part = 0.0;
-      for (int k = lane; k < j; k += 32) part = fma(bi[k], Lj[k], part);
+      double part[RPW];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) bi[j] = (bi[j] - part) / Lj[j];
+      for (int t = 0; t < RPW; t++) part[t] = 0.0;
+      for (int k = lane; k < j; k += 32) {
+        const double lv = Lj[k];
+#pragma unroll
+        for (int t = 0; t < RPW; t++) {
+          const int i = warp + t * NW;
+          if (i < q) part[t] = fma(brow[(size_t)i * r + k], lv, part[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < RPW; t++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
+      if (lane == 0) {
+        const double ljj = Lj[j];
+#pragma unroll
+        for (int t = 0; t < RPW; t++) {
+          const int i = warp + t * NW;
+          if (i < q) brow[(size_t)i * r + j] = (brow[(size_t)i * r + j] - part[t]) / ljj;
+        }
+      }
       __syncwarp();
     }
   }

@@ -261,17 +261,38 @@ sample_reduce_bwd_kernel(SRParams p, int chunk) {
   }
   __syncthreads();
   // ---- gSxb = gB_tot L_base^{-1}: backward substitution, one warp per row
-  for (int i = warp; i < q; i += NW) {
-    double* gi = gy + (size_t)i * r;
+  //      (the rows of a warp advance together: each -- strided -- factor entry is loaded once for all of them; per row the
+  //      arithmetic is unchanged, see the forward kernel)
+  {
+    constexpr int RPW = (QMAX + NW - 1) / NW;
     for (int j = r - 1; j >= 0; j--) {
-      double part = 0.0;
-      for (int k = j + 1 + lane; k < r; k += 32) part = fma(gi[k], p.L_base[(size_t)k * r + j], part);
+      double part[RPW];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) gi[j] = (gi[j] - part) / p.L_base[(size_t)j * r + j];
+      for (int t = 0; t < RPW; t++) part[t] = 0.0;
+      for (int k = j + 1 + lane; k < r; k += 32) {
+        const double lv = p.L_base[(size_t)k * r + j];
+#pragma unroll
+        for (int t = 0; t < RPW; t++) {
+          const int i = warp + t * NW;
+          if (i < q) part[t] = fma(gy[(size_t)i * r + k], lv, part[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < RPW; t++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
+      if (lane == 0) {
+        const double ljj = p.L_base[(size_t)j * r + j];
+#pragma unroll
+        for (int t = 0; t < RPW; t++) {
+          const int i = warp + t * NW;
+          if (i < q) gy[(size_t)i * r + j] = (gy[(size_t)i * r + j] - part[t]) / ljj;
+        }
+      }
       __syncwarp();
     }
-    for (int j = lane; j < r; j += 32) p.gSxb[(bb * q + i) * r + j] = gi[j];
+    for (int i = warp; i < q; i += NW)
+      for (int j = lane; j < r; j += 32) p.gSxb[(bb * q + i) * r + j] = gy[(size_t)i * r + j];
   }
 }
 
