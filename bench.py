@@ -345,11 +345,20 @@ def main():
                         torch.manual_seed(0)   # the Boltzmann draw of the initial conditions uses the global RNG: same restarts,
                         optimize_acqf(acqf, **okw)   # hence the same number of rounds, in every call and every run
                         torch.cuda.synchronize()
-                        torch.manual_seed(0)
-                        t0 = _time.perf_counter()
-                        _, oval = optimize_acqf(acqf, **okw)
-                        torch.cuda.synchronize()
-                        opt = {"wall_ms": (_time.perf_counter() - t0) * 1e3, "q": spec.q, "num_restarts": spec.num_restarts,
+                        def _timed_opt():
+                            # wall clock of one call; the smaller of two (a single shot occasionally carries a ~0.2 s allocator
+                            # / graph re-capture hiccup after the memory-heavy phases before it); both are reported
+                            walls, val = [], None
+                            for _ in range(2):
+                                torch.manual_seed(0)
+                                t0 = _time.perf_counter()
+                                _, val = optimize_acqf(acqf, **okw)
+                                torch.cuda.synchronize()
+                                walls.append((_time.perf_counter() - t0) * 1e3)
+                            return min(walls), walls, val
+
+                        wall, walls, oval = _timed_opt()
+                        opt = {"wall_ms": wall, "wall_ms_calls": walls, "q": spec.q, "num_restarts": spec.num_restarts,
                                "raw_samples": spec.raw_samples, "maxiter": 50, "acq_value": float(oval),
                                "optimizer": "scipy (default): scipy's setulb stepped on the host, one fused fwd+bwd per round"}
                         # the same call with the device-resident L-BFGS-B (settings.optimizer('device'): CUDA-graph rounds)
@@ -357,11 +366,8 @@ def main():
                             torch.manual_seed(0)
                             optimize_acqf(acqf, **okw)
                             torch.cuda.synchronize()
-                            torch.manual_seed(0)
-                            t0 = _time.perf_counter()
-                            _, oval_d = optimize_acqf(acqf, **okw)
-                            torch.cuda.synchronize()
-                            opt["device_optimizer"] = {"wall_ms": (_time.perf_counter() - t0) * 1e3, "acq_value": float(oval_d)}
+                            wall_d, walls_d, oval_d = _timed_opt()
+                            opt["device_optimizer"] = {"wall_ms": wall_d, "wall_ms_calls": walls_d, "acq_value": float(oval_d)}
                 phases = {"optimize_acqf": opt,
                           "sweep_forward_only_points_per_s": pts_local_scale * args.steps / (ms_fwd * 1e-3),
                           "sweep_forward_only_ms_per_step": ms_fwd / args.steps,
