@@ -346,15 +346,11 @@ static int log_hvi_launch(int backward, const double* gout, const double* outv, 
   // resident CTAs per SM the register allocation aims at.  The kernels are latency-bound, so occupancy beats spills: backward
   // (q = m = 4) 2 CTAs = 234 registers, no spills: 45.0 ms per 524288 samples x 32 cells; 3 = 168 registers + 216-byte stack:
   // 32.6 ms; 4 = 128 registers + 368 bytes: 30.8 ms (default); 5 / 6 = 96 / 80 registers: 33.0 / 34.8 ms.  Forward: 112
-  // registers at 4 (12.9 ms), spilling at 5 / 6 (14.7 / 15.1 ms).  MCACQ_HVI_MINB = 2 | 3 selects the other backward builds.
-  static const int minb = getenv("MCACQ_HVI_MINB") ? atoi(getenv("MCACQ_HVI_MINB")) : 4;
-#define HV_BWD(MB) log_hvi_bwd_kernel<QMAX, MMAX, MB><<<blocks, 128, 0, st>>>(gout, outv, obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out)
-  if (backward) {
-    if (minb <= 2) HV_BWD(2); else if (minb == 3) HV_BWD(3); else HV_BWD(4);
-  } else {
+  // registers at 4 (12.9 ms), spilling at 5 / 6 (14.7 / 15.1 ms).  Only the chosen builds are instantiated (each costs ~40 s of ptxas).
+  if (backward)
+    log_hvi_bwd_kernel<QMAX, MMAX, 4><<<blocks, 128, 0, st>>>(gout, outv, obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out);
+  else
     log_hvi_fwd_kernel<QMAX, MMAX, 4><<<blocks, 128, 0, st>>>(obj, cl, lcl, B, q, m, nc, tau_relu, tau_max, out);
-  }
-#undef HV_BWD
   count_launch();
   MCACQ_CUDA_CHECK_LAUNCH();
   return 0;
