@@ -156,3 +156,14 @@ def test_standardize_and_normalize_transforms():
     out = learn(torch.tensor([[1.0, 5.0], [3.0, 5.0]], dtype=torch.float64))
     assert torch.allclose(out[:, 0], torch.tensor([0.0, 1.0], dtype=torch.float64))
     assert torch.allclose(out[:, 1], torch.tensor([5.0, 5.0], dtype=torch.float64))  # degenerate range untouched
+
+
+def test_fused_supported_is_a_host_only_query():
+    """`mcacq_fused_supported` (compiled limits + shared memory of the sample / reduce kernels) answers without a CUDA device."""
+    from botorch_b200 import _lib
+
+    assert _lib.fused_supported(8, 16, 1024) and _lib.fused_supported(8, 0, 512) and _lib.fused_supported(8, 512, 1024)
+    assert not _lib.fused_supported(8, _lib.MAX_R + 1, 1024)
+    assert not _lib.fused_supported(_lib.MAX_Q + 1, 16, 1024)
+    assert not _lib.fused_supported(32, 512, 1024)            # limits fine, q x r too large for the kernels' shared memory
+    assert not _lib.fused_supported(8, 16, 0) and not _lib.fused_supported(0, 16, 8)
