@@ -3,6 +3,7 @@
 //   g++ -O2 -std=c++17 -o check check.cpp && ./check
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 
 #include "../../botorch_b200/csrc/fast_math.cuh"
@@ -15,10 +16,10 @@ static double ulp_err(double got, long double want) {
   return (double)(fabsl((long double)got - want) / ulp);
 }
 
-int main() {
+int main(int argc, char** argv) {
   std::mt19937_64 rng(1);
   auto uni = [&](double a, double b) { return a + (b - a) * (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
-  const int N = 20000000;
+  const int N = argc > 1 ? atoi(argv[1]) : 20000000;   // samples per range
   double worst;
   // exp on [-708, 708] and dense near 0
   worst = 0;
